@@ -1,0 +1,319 @@
+// Shared conjugate-gradient machinery for the pressure and viscosity solves.
+//
+// The reference runs MIC(0)-PCG on explicitly assembled matrices (src/pressuresolver.cpp:521-567,
+// src/pcgsolver/pcgsolver.h:241-295); MIC(0) is a sequential recurrence.  Here the operator is a
+// matrix-free stencil over coefficient fields, the preconditioner is the (parallel) diagonal, and
+// the vectors are fp64 dense fields addressed through a list of active 8x8x8 blocks, so a solve
+// only touches memory near the liquid.  Stopping rules are the reference's (max|r| against an
+// absolute (pressure) or relative (viscosity) tolerance); parity is defined on the converged
+// solution, not on the iterate path.
+//
+// One iteration = three kernels (A: q = A s, s.q;  B: x,r update, max|r|, r.z;  C: s = z + beta s).
+// Dot products are reduced deterministically: every CTA writes one partial, and every CTA of the
+// next kernel re-reduces the (<= FLIP_CG_MAXGRID) partials in a fixed order.  Iteration scalars
+// live in two CGState slots used alternately, so no kernel reads a scalar another CTA of the same
+// launch writes, and nothing goes back to the host except a poll every `cg_chunk` iterations.
+#pragma once
+#include "sim.h"
+
+#define CG_THREADS 512  // one thread per cell of an 8x8x8 block
+
+struct BlockCell { int i, j, k; bool inside; };
+
+FLIP_D BlockCell block_cell(const Grid &g, int blk, int t) {
+    int bi = blk % g.nbx, r = blk / g.nbx;
+    int bj = r % g.nby, bk = r / g.nby;
+    BlockCell c;
+    c.i = bi * FLIP_B + (t & 7);
+    c.j = bj * FLIP_B + ((t >> 3) & 7);
+    c.k = bk * FLIP_B + (t >> 6);
+    c.inside = c.i <= g.ni && c.j <= g.nj && c.k <= g.nk;
+    return c;
+}
+
+// sum (or max) over the CTA; result valid in every thread
+template <bool MAX>
+FLIP_D double cta_reduce(double v, double *sm /*[CG_THREADS/32]*/) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = MAX ? fmax(v, u) : v + u;
+    }
+    __syncthreads();  // protect sm from a previous use
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+    for (int w = 1; w < CG_THREADS / 32; w++) r = MAX ? fmax(r, sm[w]) : r + sm[w];
+    return r;
+}
+
+// fixed-order reduction of n partials by a whole CTA; result valid in every thread
+template <bool MAX>
+FLIP_D double reduce_partials(const double *__restrict__ part, int n, double *sm) {
+    double v = 0.0;
+    for (int q = threadIdx.x; q < n; q += CG_THREADS) v = MAX ? fmax(v, part[q]) : v + part[q];
+    return cta_reduce<MAX>(v, sm);
+}
+
+struct CGParams {
+    Grid g;
+    const int *blk_list;
+    const int *blk_count;
+    double *x, *r, *s, *q;     // [NC*total]
+    double *part;              // [3*gridDim]: s.q | r.z | max|r|
+    CGState *st;               // [2]
+    int strict;                // 1: converged when max|r| < tol (pressure), 0: <= tol (viscosity)
+};
+
+// diagonal accessors
+struct DiagPressure {
+    const float4 *c;
+    FLIP_D float operator()(int, int id) const { return c[id].x; }
+};
+struct DiagViscosity {
+    const float *d; int total;
+    FLIP_D float operator()(int comp, int id) const { return d[(size_t)comp * total + id]; }
+};
+
+// r holds b on entry.  x = 0, s = M^-1 r, partials of r.s and max|r|.
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag) {
+    __shared__ double sm[CG_THREADS / 32];
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    double rz = 0.0, bm = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            float d = diag(m, id);
+            double r = d != 0.0f ? P.r[o] : 0.0;
+            double z = d != 0.0f ? r / (double)d : 0.0;
+            P.r[o] = r;
+            P.x[o] = 0.0;
+            P.s[o] = z;
+            rz += r * z;
+            bm = fmax(bm, fabs(r));
+        }
+    }
+    rz = cta_reduce<false>(rz, sm);
+    bm = cta_reduce<true>(bm, sm);
+    if (threadIdx.x == 0) {
+        P.part[gridDim.x + blockIdx.x] = rz;
+        P.part[2 * gridDim.x + blockIdx.x] = bm;
+    }
+}
+
+// single CTA: first CGState.  tol_rel > 0: tol = tol_rel * max|b| (pcgsolver.h:254-259), else tol_abs.
+static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int nparts, double tol_abs, double tol_rel, int maxit) {
+    __shared__ double sm[CG_THREADS / 32];
+    double rho = reduce_partials<false>(P.part + nparts, nparts, sm);
+    double bmax = reduce_partials<true>(P.part + 2 * nparts, nparts, sm);
+    if (threadIdx.x == 0) {
+        CGState st;
+        st.rho = rho; st.resid = bmax; st.bmax = bmax;
+        st.tol = tol_rel > 0 ? tol_rel * bmax : tol_abs;
+        st.iter = 0; st.maxit = maxit; st.fail = 0; st.pad = 0;
+        st.done = 0; st.converged = 0;
+        if (tol_rel > 0) {
+            // viscosity: zero rhs -> solution 0, success (pcgsolver.h:254-258)
+            if (bmax == 0) { st.done = 1; st.converged = 1; }
+        } else {
+            // pressure: max|b| < tol -> zero pressure (src/pressuresolver.cpp:173-175)
+            if (bmax < tol_abs) { st.done = 1; st.converged = 1; }
+        }
+        if (!st.done && (rho == 0 || rho != rho)) { st.done = 1; st.fail = 1; }
+        P.st[0] = st;
+        P.st[1] = st;
+    }
+}
+
+// phase B: alpha = rho / s.q;  x += alpha s;  r -= alpha q;  partials of r.(M^-1 r) and max|r|
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    const CGState st = P.st[parity];
+    if (st.done) return;
+    const Grid &g = P.g;
+    double sq = reduce_partials<false>(P.part, gridDim.x, sm);
+    double alpha = st.rho / sq;
+    int nb = *P.blk_count;
+    double rz = 0.0, rm = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            float d = diag(m, id);
+            if (d == 0.0f) continue;
+            size_t o = (size_t)m * g.total + id;
+            double s = P.s[o], q = P.q[o];
+            P.x[o] += alpha * s;
+            double r = P.r[o] - alpha * q;
+            P.r[o] = r;
+            rz += r * (r / (double)d);
+            rm = fmax(rm, fabs(r));
+        }
+    }
+    rz = cta_reduce<false>(rz, sm);
+    rm = cta_reduce<true>(rm, sm);
+    if (threadIdx.x == 0) {
+        P.part[gridDim.x + blockIdx.x] = rz;
+        P.part[2 * gridDim.x + blockIdx.x] = rm;
+    }
+}
+
+// phase C: convergence bookkeeping into the other CGState slot, then s = M^-1 r + beta s
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag diag, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    const CGState st = P.st[parity];
+    if (st.done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.st[parity ^ 1] = st;
+        return;
+    }
+    const Grid &g = P.g;
+    double rho_new = reduce_partials<false>(P.part + gridDim.x, gridDim.x, sm);
+    double rmax = reduce_partials<true>(P.part + 2 * gridDim.x, gridDim.x, sm);
+    bool conv = P.strict ? (rmax < st.tol) : (rmax <= st.tol);
+    bool bad = rmax != rmax;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CGState nx = st;
+        nx.iter = st.iter + 1;
+        nx.resid = rmax;
+        nx.rho = rho_new;
+        nx.converged = conv ? 1 : 0;
+        nx.done = (conv || bad || nx.iter >= st.maxit) ? 1 : 0;
+        if (bad) nx.fail = 1;
+        P.st[parity ^ 1] = nx;
+    }
+    if (conv || bad) return;
+    double beta = rho_new / st.rho;
+    int nb = *P.blk_count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            float d = diag(m, id);
+            if (d == 0.0f) continue;
+            size_t o = (size_t)m * g.total + id;
+            P.s[o] = P.r[o] / (double)d + beta * P.s[o];
+        }
+    }
+}
+
+// zero a [NC*total] double field on the cells of the listed blocks
+template <int NC>
+__global__ void __launch_bounds__(CG_THREADS) k_clear_blocks(Grid g, const int *__restrict__ list,
+                                                              const int *__restrict__ count, double *__restrict__ f) {
+    int nb = *count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) f[(size_t)m * g.total + id] = 0.0;
+    }
+}
+
+// ---- active block list -------------------------------------------------------------------
+// flag[b] = 1 if any of the NC diagonal fields is non-zero inside block b
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_flag_blocks(Grid g, Diag diag, int *__restrict__ flag) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    BlockCell c = block_cell(g, blockIdx.x, threadIdx.x);
+    bool nz = false;
+    if (c.inside) {
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) nz = nz || diag(m, id) != 0.0f;
+    }
+    if (nz) any = 1;  // benign same-value race
+    __syncthreads();
+    if (threadIdx.x == 0) flag[blockIdx.x] = any;
+}
+
+// single CTA, ordered compaction (ascending block id => deterministic CTA/block assignment)
+static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__restrict__ flag, int n, int *__restrict__ list,
+                                                         int *__restrict__ count) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int id = base + threadIdx.x;
+        int v = (id < n && flag[id]) ? 1 : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        int pos = carry_s + inc - v + (wid > 0 ? warp_sums[wid - 1] : 0);
+        if (v) list[pos] = id;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = pos + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry_s;
+}
+
+static inline int cg_grid(const Sim &s) {
+    int gsz = s.num_sms * 2;
+    return gsz > FLIP_CG_MAXGRID ? FLIP_CG_MAXGRID : gsz;
+}
+
+template <int NC, class Diag>
+static void build_block_list(Sim &s, Diag diag) {
+    const Grid &g = s.g;
+    auto kflag = &k_flag_blocks<NC, Diag>;
+    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count);
+    s.kernel_launches += 2;
+    KERNEL_CHECK();
+}
+
+// Generic driver.  `apply(parity)` launches the phase-A kernel (q = A s and the s.q partials).
+template <int NC, class Diag, class ApplyFn>
+static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply) {
+    int G = cg_grid(s);
+    auto kinit = &k_cg_init<NC, Diag>;
+    auto kupdate = &k_cg_update<NC, Diag>;
+    auto kdir = &k_cg_direction<NC, Diag>;
+    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
+    s.kernel_launches += 2;
+    KERNEL_CHECK();
+    int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
+    CGState h;
+    int launched = 0;
+    while (true) {
+        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h = *s.cgst_host;
+        if (h.done || launched >= maxit + chunk) break;
+        for (int it = 0; it < chunk; it++) {
+            int parity = it & 1;
+            apply(parity);
+            FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
+            FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
+            s.kernel_launches += 3;
+        }
+        KERNEL_CHECK();
+        launched += chunk;
+    }
+    return h;
+}

@@ -1,0 +1,157 @@
+// Variational free-surface pressure projection.
+//
+// Reference behaviour being reproduced (relative to /root/reference):
+//   unknown set, rhs, coefficients   src/pressuresolver.cpp:196-322
+//   CG stopping rule                  src/pressuresolver.cpp:521-567 (max|r| < 1e-9 absolute)
+//   result cast to float              src/pressuresolver.cpp:186-191
+//   _project                          src/fluidsimulation.cpp:522-531
+//
+// The reference assembles {diag,+i,+j,+k} per unknown and addresses neighbours through a dense
+// int keymap with a sequential MIC(0) preconditioner.  Here the same four float coefficients are
+// a dense float4 stencil field (one 16-byte load per cell), the operator is applied matrix-free
+// on the active 8x8x8 blocks, and the preconditioner is the diagonal (see cg.h).
+#include "cg.h"
+#include "levelset_math.h"
+
+// rhs (into r) and stencil coefficients for every cell; non-unknown cells get zeros.
+__global__ void __launch_bounds__(256) k_pressure_build(Grid g, const float *__restrict__ phi, const float *__restrict__ vel,
+                                                        const float *__restrict__ weight, float4 *__restrict__ coef,
+                                                        double *__restrict__ rhs, float scale, float minfrac) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
+    size_t T = (size_t)g.total;
+    float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    double b = 0.0;
+    // unknowns: interior cells with phi < 0 (src/pressuresolver.cpp:206-215)
+    bool unknown = i >= 1 && i < g.ni - 1 && j >= 1 && j < g.nj - 1 && k >= 1 && k < g.nk - 1 && phi[id] < 0;
+    if (unknown) {
+        const float *wu = weight, *wv = weight + T, *ww = weight + 2 * T;
+        const float *u = vel, *v = vel + T, *w = vel + 2 * T;
+        // negative divergence (src/pressuresolver.cpp:235-244): float products, double accumulation
+        b -= (double)(wu[id + 1] * u[id + 1]);
+        b += (double)(wu[id] * u[id]);
+        b -= (double)(wv[id + sy] * v[id + sy]);
+        b += (double)(wv[id] * v[id]);
+        b -= (double)(ww[id + sz] * w[id + sz]);
+        b += (double)(ww[id] * w[id]);
+        b /= g.dxd;
+        float p0 = phi[id];
+        // coefficients (src/pressuresolver.cpp:259-320), float accumulation in the reference's order
+        float term = wu[id + 1] * scale;
+        float pn = phi[id + 1];
+        if (pn < 0) { c.x += term; c.y -= term; }
+        else { c.x += term / fmaxf(frac_inside2(p0, pn), minfrac); }
+        term = wu[id] * scale;
+        pn = phi[id - 1];
+        if (pn < 0) { c.x += term; }
+        else { c.x += term / fmaxf(frac_inside2(pn, p0), minfrac); }
+        term = wv[id + sy] * scale;
+        pn = phi[id + sy];
+        if (pn < 0) { c.x += term; c.z -= term; }
+        else { c.x += term / fmaxf(frac_inside2(p0, pn), minfrac); }
+        term = wv[id] * scale;
+        pn = phi[id - sy];
+        if (pn < 0) { c.x += term; }
+        else { c.x += term / fmaxf(frac_inside2(pn, p0), minfrac); }
+        term = ww[id + sz] * scale;
+        pn = phi[id + sz];
+        if (pn < 0) { c.x += term; c.w -= term; }
+        else { c.x += term / fmaxf(frac_inside2(p0, pn), minfrac); }
+        term = ww[id] * scale;
+        pn = phi[id - sz];
+        if (pn < 0) { c.x += term; }
+        else { c.x += term / fmaxf(frac_inside2(pn, p0), minfrac); }
+    }
+    coef[id] = c;
+    rhs[id] = b;
+}
+
+// phase A: q = A s on the active blocks (row order of src/pressuresolver.cpp:464-499) and s.q partials
+__global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const float4 *__restrict__ coef, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (P.st[parity].done) return;
+    const Grid &g = P.g;
+    const int sy = SY(g), sz = SZ(g);
+    const double *__restrict__ s = P.s;
+    int nb = *P.blk_count;
+    double sq = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        float4 a = coef[id];
+        if (a.x == 0.0f) continue;
+        double sc = s[id];
+        double val = 0.0;
+        val += s[id - 1] * (double)coef[id - 1].y;
+        val += s[id + 1] * (double)a.y;
+        val += s[id - sy] * (double)coef[id - sy].z;
+        val += s[id + sy] * (double)a.z;
+        val += s[id - sz] * (double)coef[id - sz].w;
+        val += s[id + sz] * (double)a.w;
+        val += sc * (double)a.x;
+        P.q[id] = val;
+        sq += sc * val;
+    }
+    sq = cta_reduce<false>(sq, sm);
+    if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
+}
+
+__global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const double *__restrict__ x, float *__restrict__ pr) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni, g.nj, g.nk, i, j, k)) return;
+    int id = gidx(g, i, j, k);
+    pr[id] = coef[id].x != 0.0f ? (float)x[id] : 0.0f;
+}
+
+void solve_pressure(Sim &s, float dt) {
+    const Grid &g = s.g;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, s.stream));
+    // scale = deltaTime / (dx*dx) in double, used as (float)scale (src/pressuresolver.cpp:250, 259)
+    double scale = (double)dt / (g.dxd * g.dxd);
+    long long nf = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
+    FLIP_LAUNCH(k_pressure_build, cdiv(nf, 256), 256, s.stream, g, (const float *)s.phi_liq, (const float *)s.vel,
+                (const float *)s.weight, s.pcoef, s.cg_r, (float)scale, s.minfrac);
+    s.kernel_launches++;
+    DiagPressure diag{s.pcoef};
+    build_block_list<1>(s, diag);
+    // the search direction is read with a one-cell halo: it must be zero outside the active blocks
+    CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * (size_t)g.total, s.stream));
+    CGParams P;
+    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count;
+    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q;
+    P.part = s.part; P.st = s.cgst; P.strict = 1;
+    int G = cg_grid(s);
+    const float4 *coef = s.pcoef;
+    cudaStream_t st = s.stream;
+    CGState h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, s.pressure_maxit * s.pressure_maxit_scale, [&](int parity) {
+        FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, P, coef, parity);
+    });
+    long long nc = (long long)g.ni * g.nj * g.nk;
+    FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);
+    s.kernel_launches++;
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaEventRecord(e1, s.stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
+    s.pres_stats.iters = h.iter; s.pres_stats.converged = h.converged; s.pres_stats.resid = h.resid;
+    s.pres_stats.bmax = h.bmax; s.pres_stats.skipped = (h.iter == 0 && h.converged) ? 1 : 0;
+    s.pres_stats.unknowns = *s.count_host;  // active blocks (the unknown count is not materialised)
+    s.pres_stats.ms = ms;
+    if (s.verbose) {
+        printf("\tpressure: %d iterations, max|r| %.3e, %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,
+               h.converged ? "converged" : "NOT converged", *s.count_host, ms);
+    }
+}
+
+// _project (src/fluidsimulation.cpp:522-531); the weights are static and precomputed
+void stage_project(Sim &s, float dt) {
+    solve_pressure(s, dt);
+    apply_pressure(s, dt);
+    extrapolate_velocity(s);
+}

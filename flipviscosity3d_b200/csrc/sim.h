@@ -1,0 +1,129 @@
+// Device-resident simulation state and the stage entry points (host side of the kernels).
+#pragma once
+#include "grid.h"
+#include <string>
+#include <vector>
+
+struct CGState {
+    double rho;      // r.z of the current iterate
+    double resid;    // max|r|
+    double tol;      // absolute tolerance on max|r|
+    double bmax;     // max|b|
+    int iter;
+    int done;        // 1 = stop iterating
+    int converged;   // 1 = resid under tol
+    int maxit;
+    int fail;        // 1 = rho was 0/NaN at start (pcgsolver.h:264-267)
+    int pad;
+};
+
+struct SolveStats {
+    int iters; int converged; int unknowns; int skipped; double resid; double bmax; float ms;
+};
+
+#define FLIP_CG_MAXGRID 1024  // upper bound on the persistent CG grid (partials per reduction)
+
+struct Sim {
+    Grid g;
+    cudaStream_t stream = 0;
+    int num_sms = 1;
+    std::string last_error;
+
+    // --- parameters (reference defaults: src/fluidsimulation.h:121-130) ---
+    float gravity[3] = {0.0f, -9.81f, 0.0f};
+    float cfl_number = 5.0f;
+    float minfrac = 0.01f;
+    float pic_ratio = 0.05f;
+    float particle_radius = 0.0f;       // (float)(dx*1.01*sqrt(3)/2), src/fluidsimulation.cpp:36
+    int extrap_layers = 7;              // ceil(CFL)+2, src/fluidsimulation.cpp:692
+    double pressure_tol = 1e-9;         // absolute, src/pressuresolver.h:224
+    int pressure_maxit = 200;           // the reference's MICCG(0) cap (pressuresolver.h:225)
+    int pressure_maxit_scale = 40;      // this library's Jacobi-PCG is allowed maxit*scale iterations
+    double visc_tol = 1e-6;             // relative to max|rhs|, src/viscositysolver.h:200
+    double visc_accept = 10.0;          // src/viscositysolver.h:201
+    int visc_maxit = 700;               // src/viscositysolver.h:202
+    int visc_maxit_scale = 40;
+    int cg_chunk = 16;                  // CG iterations launched between host convergence polls
+    int verbose = 0;
+    bool viscosity_nonzero = true;      // reference initial viscosity is 1.0 everywhere
+
+    // --- particles (SoA, cell-binned every substep) ---
+    long long np = 0, cap = 0;
+    float *p[2][6] = {{0}};   // [buffer][px,py,pz,vx,vy,vz]
+    unsigned *pid[2] = {0, 0};
+    int cur = 0;              // active particle buffer
+    int *cell_of = 0;         // padded cell index per particle
+    int *cell_start = 0;      // [total+1] exclusive scan of counts (padded layout)
+    int *cell_cursor = 0;     // [total]
+    int *scan_tmp = 0;
+    bool binned = false;
+
+    // --- fields, all in the padded layout, 3-component arrays are [3*total] ---
+    float *phi_liq = 0;       // cell-centred liquid SDF
+    float *phi_sol = 0;       // nodal solid SDF
+    float *sol_center = 0;    // solid SDF at cell centres (mean of 8 nodes)
+    float *vel = 0;           // MAC velocity U,V,W
+    float *saved = 0;         // copy taken after P2G+extrapolation
+    float *weight = 0;        // solid face weights (static)
+    unsigned char *valid = 0; // per face validity
+    unsigned char *layer = 0; // extrapolation layer id per face
+    unsigned char *fstate = 0;// viscosity face state (1 = solid, 0 = fluid), static
+    float *viscosity = 0;     // (ni+1)(nj+1)(nk+1) grid
+    float *pressure = 0;      // float pressure of the last projection
+    float *maxvel_dev = 0;    // [1] max |u| over faces
+    float *maxvel_host = 0;   // pinned
+
+    // --- solver workspaces ---
+    float4 *pcoef = 0;        // pressure stencil {diag, +i, +j, +k}
+    double *cg_x = 0, *cg_r = 0, *cg_s = 0, *cg_q = 0;   // [3*total] (pressure uses component 0)
+    float *vvol = 0;          // 7 volume grids [7*total]: center,U,V,W,edgeU,edgeV,edgeW
+    float *vnode = 0;         // 7 nodal phi grids [7*total]
+    unsigned char *vvalid = 0;// dilated liquid mask
+    float *vcoef = 0;         // 4 coefficient grids [4*total]: center, edgeU, edgeV, edgeW
+    float *vdiag = 0;         // [3*total] row diagonals (0 = not an unknown)
+    int *blk_flag = 0;        // [nblocks]
+    int *blk_list = 0;        // [nblocks]
+    int *blk_count = 0;       // [1]
+    double *part = 0;         // [4*FLIP_CG_MAXGRID] reduction partials
+    CGState *cgst = 0;        // [2] ping-pong
+    CGState *cgst_host = 0;   // pinned
+    int *count_host = 0;      // pinned
+
+    // stats of the last substep
+    SolveStats pres_stats = {0, 0, 0, 0, 0, 0, 0};
+    SolveStats visc_stats = {0, 0, 0, 0, 0, 0, 0};
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long substeps = 0;
+    long long kernel_launches = 0;
+
+    float *vc(int c) { return vel + (size_t)c * g.total; }
+};
+
+// api.cu
+void sim_alloc(Sim &s, int ni, int nj, int nk, float dx);
+void sim_free(Sim &s);
+void sim_reserve_particles(Sim &s, long long n);
+
+// fields.cu
+void solid_precompute(Sim &s);               // weights, cell-centre solid phi, face states
+void stage_add_body_force(Sim &s, float dt);
+void extrapolate_velocity(Sim &s);
+void stage_constrain(Sim &s);
+float compute_max_velocity(Sim &s);
+void apply_pressure(Sim &s, float dt);
+
+// particles.cu
+void bin_particles(Sim &s);
+void stage_update_liquid_sdf(Sim &s);
+void stage_advect_velocity_field(Sim &s);    // P2G + mask + extrapolate + save
+void stage_advect_particles(Sim &s, float dt);
+
+// pressure.cu / viscosity.cu
+void stage_project(Sim &s, float dt);
+void solve_pressure(Sim &s, float dt);
+void stage_apply_viscosity(Sim &s, float dt);
+void viscosity_volumes(Sim &s);
+
+// substep driver (api.cu)
+void sim_substep(Sim &s, float dt);
+int sim_advance(Sim &s, float dt);

@@ -1,0 +1,350 @@
+// Variational viscosity (Batty & Bridson 2008) as a matrix-free coupled U/V/W face stencil.
+//
+// Reference behaviour being reproduced (relative to /root/reference):
+//   face states           src/viscositysolver.cpp:80-123   (static, see fields.cu)
+//   volume fractions      src/viscositysolver.cpp:135-270
+//   unknown set           src/viscositysolver.cpp:276-366
+//   rows / rhs            src/viscositysolver.cpp:374-664
+//   solve + acceptance    src/viscositysolver.cpp:666-690, src/pcgsolver/pcgsolver.h:241-295
+//   write-back            src/viscositysolver.cpp:692-727
+//
+// The reference assembles a vector-of-vectors sparse matrix (<= 15 nnz/row).  Here every row is
+// recomputed from four coefficient fields (2*f*mu*vol at cell centres, f*mu_bar*vol on the three
+// edge families) shared by the three unknowns of a cell, plus one diagonal per face.  Off-diagonal
+// masks are not needed: the search direction is kept at exactly 0 on non-unknown faces, which is
+// what the reference's "drop FLUID neighbours without an index, move SOLID neighbours to the rhs"
+// amounts to inside A*s.
+#include "cg.h"
+#include "levelset_math.h"
+
+// volume grid ids
+enum { VC = 0, VU = 1, VV = 2, VW = 3, VEU = 4, VEV = 5, VEW = 6 };
+
+struct VolGrid { int w, h, d; float csx, csy, csz; };
+
+__device__ __host__ inline VolGrid vol_grid(const Grid &g, int v) {
+    // dims: src/viscositysolver.h:68-76; centerStart offsets: src/viscositysolver.cpp:170-177
+    VolGrid r;
+    const float h = g.hdx;
+    switch (v) {
+        case VC:  r.w = g.ni;     r.h = g.nj;     r.d = g.nk;     r.csx = h; r.csy = h; r.csz = h; break;
+        case VU:  r.w = g.ni + 1; r.h = g.nj;     r.d = g.nk;     r.csx = 0; r.csy = h; r.csz = h; break;
+        case VV:  r.w = g.ni;     r.h = g.nj + 1; r.d = g.nk;     r.csx = h; r.csy = 0; r.csz = h; break;
+        case VW:  r.w = g.ni;     r.h = g.nj;     r.d = g.nk + 1; r.csx = h; r.csy = h; r.csz = 0; break;
+        case VEU: r.w = g.ni;     r.h = g.nj + 1; r.d = g.nk + 1; r.csx = h; r.csy = 0; r.csz = 0; break;
+        case VEV: r.w = g.ni + 1; r.h = g.nj;     r.d = g.nk + 1; r.csx = 0; r.csy = h; r.csz = 0; break;
+        default:  r.w = g.ni + 1; r.h = g.nj + 1; r.d = g.nk;     r.csx = 0; r.csy = 0; r.csz = h; break;
+    }
+    return r;
+}
+
+// liquid cells dilated twice in 6-connectivity on the (ni+1)(nj+1)(nk+1) index box
+// (src/viscositysolver.cpp:138-168) = cells within L1 distance 2 of a cell with phi < 0
+__global__ void __launch_bounds__(256) k_visc_valid(Grid g, const float *__restrict__ phi, unsigned char *__restrict__ vvalid) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    bool v = false;
+    for (int dk = -2; dk <= 2 && !v; dk++) {
+        int rj = 2 - abs(dk);
+        for (int dj = -rj; dj <= rj && !v; dj++) {
+            int ri = rj - abs(dj);
+            for (int di = -ri; di <= ri; di++) {
+                int a = i + di, b = j + dj, c = k + dk;
+                if (a >= 0 && b >= 0 && c >= 0 && a < g.ni && b < g.nj && c < g.nk && phi[gidx(g, a, b, c)] < 0) {
+                    v = true;
+                    break;
+                }
+            }
+        }
+    }
+    vvalid[gidx(g, i, j, k)] = v ? 1 : 0;
+}
+
+// nodal phi of the 7 control-volume families.  The reference caches node values first-come in
+// k,j,i scan order, each computed from the position arithmetic of the cell that got there first
+// (src/viscositysolver.cpp:188-252); the same cell and the same float expression are used here.
+__global__ void __launch_bounds__(256) k_visc_nodes(Grid g, const float *__restrict__ phi, const unsigned char *__restrict__ vvalid,
+                                                    float *__restrict__ vnode) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 2, g.nj + 2, g.nk + 2, i, j, k)) return;
+    int id = gidx(g, i, j, k);
+    for (int v = 0; v < 7; v++) {
+        VolGrid vg = vol_grid(g, v);
+        if (i > vg.w || j > vg.h || k > vg.d) continue;
+        float val = 0.0f;
+        bool found = false;
+        for (int n = 0; n < 8 && !found; n++) {
+            // scan order: smallest k first, then j, then i  ->  offsets (1,1,1),(0,1,1),(1,0,1),...
+            int a = (n & 1) ? 0 : 1, b = (n & 2) ? 0 : 1, c = (n & 4) ? 0 : 1;
+            int ci = i - a, cj = j - b, ck = k - c;
+            if (ci < 0 || cj < 0 || ck < 0 || ci >= vg.w || cj >= vg.h || ck >= vg.d) continue;
+            if (!vvalid[gidx(g, ci, cj, ck)]) continue;
+            found = true;
+            // centre = centerStart + GridIndexToCellCenter(ci,cj,ck); node = centre +- hdx
+            float cx = vg.csx + index_to_center(ci, g.dxd);
+            float cy = vg.csy + index_to_center(cj, g.dxd);
+            float cz = vg.csz + index_to_center(ck, g.dxd);
+            float px = cx + (a ? g.hdx : -g.hdx);
+            float py = cy + (b ? g.hdx : -g.hdx);
+            float pz = cz + (c ? g.hdx : -g.hdx);
+            // ParticleLevelSet::trilinearInterpolate (src/particlelevelset.cpp:88-92)
+            val = (float)trilinear_grid(g, phi, g.ni, g.nj, g.nk, px - g.hdx, py - g.hdx, pz - g.hdx);
+        }
+        vnode[(size_t)v * g.total + id] = val;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_visc_volumes(Grid g, const unsigned char *__restrict__ vvalid,
+                                                      const float *__restrict__ vnode, float *__restrict__ vvol) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
+    bool valid = vvalid[id] != 0;
+    for (int v = 0; v < 7; v++) {
+        VolGrid vg = vol_grid(g, v);
+        if (i >= vg.w || j >= vg.h || k >= vg.d) continue;
+        float out = 0.0f;
+        if (valid) {
+            const float *nd = vnode + (size_t)v * g.total;
+            float p000 = nd[id], p100 = nd[id + 1], p010 = nd[id + sy], p110 = nd[id + 1 + sy];
+            float p001 = nd[id + sz], p101 = nd[id + 1 + sz], p011 = nd[id + sy + sz], p111 = nd[id + 1 + sy + sz];
+            if (p000 < 0 && p001 < 0 && p010 < 0 && p011 < 0 && p100 < 0 && p101 < 0 && p110 < 0 && p111 < 0) out = 1.0f;
+            else if (p000 >= 0 && p001 >= 0 && p010 >= 0 && p011 >= 0 && p100 >= 0 && p101 >= 0 && p110 >= 0 && p111 >= 0) out = 0.0f;
+            else out = cube_fraction(p000, p100, p010, p110, p001, p101, p011, p111);
+        }
+        vvol[(size_t)v * g.total + id] = out;
+    }
+}
+
+void viscosity_volumes(Sim &s) {
+    const Grid &g = s.g;
+    long long n1 = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
+    long long n2 = (long long)(g.ni + 2) * (g.nj + 2) * (g.nk + 2);
+    FLIP_LAUNCH(k_visc_valid, cdiv(n1, 256), 256, s.stream, g, (const float *)s.phi_liq, s.vvalid);
+    FLIP_LAUNCH(k_visc_nodes, cdiv(n2, 256), 256, s.stream, g, (const float *)s.phi_liq, (const unsigned char *)s.vvalid, s.vnode);
+    FLIP_LAUNCH(k_visc_volumes, cdiv(n1, 256), 256, s.stream, g, (const unsigned char *)s.vvalid, (const float *)s.vnode, s.vvol);
+    s.kernel_launches += 3;
+    KERNEL_CHECK();
+}
+
+// coefficient fields: cc = 2*f*mu*vol_center, ceu/cev/cew = f*mu_bar*vol_edge{U,V,W}
+__global__ void __launch_bounds__(256) k_visc_coefs(Grid g, const float *__restrict__ visc, const float *__restrict__ vvol,
+                                                    float *__restrict__ vcoef, float factor) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
+    size_t T = (size_t)g.total;
+    float mu = visc[id];
+    // 2 * factor * visc * vol (src/viscositysolver.cpp:422-423)
+    vcoef[id] = 2 * factor * mu * vvol[VC * T + id];
+    // edge means: the four cells sharing the edge (src/viscositysolver.cpp:397-413 for U rows)
+    float mu_w = 0.25f * (visc[id - 1] + visc[id - 1 - sy] + mu + visc[id - sy]);
+    float mu_v = 0.25f * (visc[id - 1] + visc[id - 1 - sz] + mu + visc[id - sz]);
+    float mu_u = 0.25f * (visc[id - sy] + visc[id - sy - sz] + mu + visc[id - sz]);
+    vcoef[1 * T + id] = factor * mu_u * vvol[VEU * T + id];
+    vcoef[2 * T + id] = factor * mu_v * vvol[VEV * T + id];
+    vcoef[3 * T + id] = factor * mu_w * vvol[VEW * T + id];
+}
+
+// rows: unknown test, diagonal, rhs (rhs goes to r)
+__global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restrict__ vvol, const float *__restrict__ vcoef,
+                                                   const unsigned char *__restrict__ fstate, const float *__restrict__ vel,
+                                                   float *__restrict__ vdiag, double *__restrict__ rhs) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
+    size_t T = (size_t)g.total;
+    const float *cc = vcoef, *cu = vcoef + T, *cv = vcoef + 2 * T, *cw = vcoef + 3 * T;
+    const float *vc = vvol + VC * T, *veu = vvol + VEU * T, *vev = vvol + VEV * T, *vew = vvol + VEW * T;
+    const unsigned char *su = fstate, *sv = fstate + T, *sw = fstate + 2 * T;
+    const float *u = vel, *v = vel + T, *w = vel + 2 * T;
+    bool interior = i >= 1 && i < g.ni && j >= 1 && j < g.nj && k >= 1 && k < g.nk;
+    float dU = 0, dV = 0, dW = 0;
+    double bU = 0, bV = 0, bW = 0;
+    if (interior && su[id] == 0) {
+        float vol = vvol[VU * T + id];
+        if (vol > 0 || vc[id] > 0 || vc[id - 1] > 0 || vew[id + sy] > 0 || vew[id] > 0 || vev[id + sz] > 0 || vev[id] > 0) {
+            float fR = cc[id], fL = cc[id - 1], fT = cw[id + sy], fB = cw[id], fF = cv[id + sz], fK = cv[id];
+            dU = vol + fR + fL + fT + fB + fF + fK;
+            float r = vol * u[id];
+            if (su[id + 1]) r -= -fR * u[id + 1];
+            if (su[id - 1]) r -= -fL * u[id - 1];
+            if (su[id + sy]) r -= -fT * u[id + sy];
+            if (su[id - sy]) r -= -fB * u[id - sy];
+            if (su[id + sz]) r -= -fF * u[id + sz];
+            if (su[id - sz]) r -= -fK * u[id - sz];
+            if (sv[id + sy]) r -= -fT * v[id + sy];
+            if (sv[id - 1 + sy]) r -= fT * v[id - 1 + sy];
+            if (sv[id]) r -= fB * v[id];
+            if (sv[id - 1]) r -= -fB * v[id - 1];
+            if (sw[id + sz]) r -= -fF * w[id + sz];
+            if (sw[id - 1 + sz]) r -= fF * w[id - 1 + sz];
+            if (sw[id]) r -= fK * w[id];
+            if (sw[id - 1]) r -= -fK * w[id - 1];
+            bU = (double)r;
+        }
+    }
+    if (interior && sv[id] == 0) {
+        float vol = vvol[VV * T + id];
+        if (vol > 0 || vew[id + 1] > 0 || vew[id] > 0 || vc[id] > 0 || vc[id - sy] > 0 || veu[id + sz] > 0 || veu[id] > 0) {
+            float fR = cw[id + 1], fL = cw[id], fT = cc[id], fB = cc[id - sy], fF = cu[id + sz], fK = cu[id];
+            dV = vol + fR + fL + fT + fB + fF + fK;
+            float r = vol * v[id];
+            if (sv[id + 1]) r -= -fR * v[id + 1];
+            if (sv[id - 1]) r -= -fL * v[id - 1];
+            if (sv[id + sy]) r -= -fT * v[id + sy];
+            if (sv[id - sy]) r -= -fB * v[id - sy];
+            if (sv[id + sz]) r -= -fF * v[id + sz];
+            if (sv[id - sz]) r -= -fK * v[id - sz];
+            if (su[id + 1]) r -= -fR * u[id + 1];
+            if (su[id + 1 - sy]) r -= fR * u[id + 1 - sy];
+            if (su[id]) r -= fL * u[id];
+            if (su[id - sy]) r -= -fL * u[id - sy];
+            if (sw[id + sz]) r -= -fF * w[id + sz];
+            if (sw[id - sy + sz]) r -= fF * w[id - sy + sz];
+            if (sw[id]) r -= fK * w[id];
+            if (sw[id - sy]) r -= -fK * w[id - sy];
+            bV = (double)r;
+        }
+    }
+    if (interior && sw[id] == 0) {
+        float vol = vvol[VW * T + id];
+        if (vol > 0 || vev[id + 1] > 0 || vev[id] > 0 || veu[id + sy] > 0 || veu[id] > 0 || vc[id] > 0 || vc[id - sz] > 0) {
+            float fR = cv[id + 1], fL = cv[id], fT = cu[id + sy], fB = cu[id], fF = cc[id], fK = cc[id - sz];
+            dW = vol + fR + fL + fT + fB + fF + fK;
+            float r = vol * w[id];
+            if (sw[id + 1]) r -= -fR * w[id + 1];
+            if (sw[id - 1]) r -= -fL * w[id - 1];
+            if (sw[id + sy]) r -= -fT * w[id + sy];
+            if (sw[id - sy]) r -= -fB * w[id - sy];
+            if (sw[id + sz]) r -= -fF * w[id + sz];
+            if (sw[id - sz]) r -= -fK * w[id - sz];
+            if (su[id + 1]) r -= -fR * u[id + 1];
+            if (su[id + 1 - sz]) r -= fR * u[id + 1 - sz];
+            if (su[id]) r -= fL * u[id];
+            if (su[id - sz]) r -= -fL * u[id - sz];
+            if (sv[id + sy]) r -= -fT * v[id + sy];
+            if (sv[id + sy - sz]) r -= fT * v[id + sy - sz];
+            if (sv[id]) r -= fB * v[id];
+            if (sv[id - sz]) r -= -fB * v[id - sz];
+            bW = (double)r;
+        }
+    }
+    vdiag[id] = dU; vdiag[T + id] = dV; vdiag[2 * T + id] = dW;
+    rhs[id] = dU != 0.0f ? bU : 0.0;
+    rhs[T + id] = dV != 0.0f ? bV : 0.0;
+    rhs[2 * T + id] = dW != 0.0f ? bW : 0.0;
+}
+
+// phase A: q = A s for the three face families of each cell index
+__global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const float *__restrict__ vcoef,
+                                                           const float *__restrict__ vdiag, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (P.st[parity].done) return;
+    const Grid &g = P.g;
+    const int sy = SY(g), sz = SZ(g);
+    const size_t T = (size_t)g.total;
+    const float *__restrict__ cc = vcoef, *__restrict__ cu = vcoef + T, *__restrict__ cv = vcoef + 2 * T,
+                *__restrict__ cw = vcoef + 3 * T;
+    const double *__restrict__ su = P.s, *__restrict__ sv = P.s + T, *__restrict__ sw = P.s + 2 * T;
+    int nb = *P.blk_count;
+    double sq = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        float dU = vdiag[id], dV = vdiag[T + id], dW = vdiag[2 * T + id];
+        if (dU == 0.0f && dV == 0.0f && dW == 0.0f) continue;
+        double u0 = su[id], v0 = sv[id], w0 = sw[id];
+        if (dU != 0.0f) {
+            double fR = cc[id], fL = cc[id - 1], fT = cw[id + sy], fB = cw[id], fF = cv[id + sz], fK = cv[id];
+            double q = (double)dU * u0 - fR * su[id + 1] - fL * su[id - 1] - fT * su[id + sy] - fB * su[id - sy] -
+                       fF * su[id + sz] - fK * su[id - sz] - fT * sv[id + sy] + fT * sv[id - 1 + sy] + fB * v0 -
+                       fB * sv[id - 1] - fF * sw[id + sz] + fF * sw[id - 1 + sz] + fK * w0 - fK * sw[id - 1];
+            P.q[id] = q;
+            sq += u0 * q;
+        }
+        if (dV != 0.0f) {
+            double fR = cw[id + 1], fL = cw[id], fT = cc[id], fB = cc[id - sy], fF = cu[id + sz], fK = cu[id];
+            double q = (double)dV * v0 - fR * sv[id + 1] - fL * sv[id - 1] - fT * sv[id + sy] - fB * sv[id - sy] -
+                       fF * sv[id + sz] - fK * sv[id - sz] - fR * su[id + 1] + fR * su[id + 1 - sy] + fL * u0 -
+                       fL * su[id - sy] - fF * sw[id + sz] + fF * sw[id - sy + sz] + fK * w0 - fK * sw[id - sy];
+            P.q[T + id] = q;
+            sq += v0 * q;
+        }
+        if (dW != 0.0f) {
+            double fR = cv[id + 1], fL = cv[id], fT = cu[id + sy], fB = cu[id], fF = cc[id], fK = cc[id - sz];
+            double q = (double)dW * w0 - fR * sw[id + 1] - fL * sw[id - 1] - fT * sw[id + sy] - fB * sw[id - sy] -
+                       fF * sw[id + sz] - fK * sw[id - sz] - fR * su[id + 1] + fR * su[id + 1 - sz] + fL * u0 -
+                       fL * su[id - sz] - fT * sv[id + sy] + fT * sv[id + sy - sz] + fB * v0 - fB * sv[id - sz];
+            P.q[2 * T + id] = q;
+            sq += w0 * q;
+        }
+    }
+    sq = cta_reduce<false>(sq, sm);
+    if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
+}
+
+// _applySolutionToVelocityField: the whole field is cleared, unknowns get (float)soln
+__global__ void __launch_bounds__(256) k_visc_store(Grid g, const float *__restrict__ vdiag, const double *__restrict__ x, float *__restrict__ vel) {
+    int i, j, k;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+    int id = gidx(g, i, j, k);
+    size_t T = (size_t)g.total;
+    for (int c = 0; c < 3; c++) {
+        int w = g.ni + (c == 0), h = g.nj + (c == 1), d = g.nk + (c == 2);
+        if (i >= w || j >= h || k >= d) continue;
+        vel[c * T + id] = vdiag[c * T + id] != 0.0f ? (float)x[c * T + id] : 0.0f;
+    }
+}
+
+void stage_apply_viscosity(Sim &s, float dt) {
+    s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0};
+    if (!s.viscosity_nonzero) return;  // src/fluidsimulation.cpp:171-184
+    const Grid &g = s.g;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, s.stream));
+    viscosity_volumes(s);
+    // factor = dt * invdx * invdx in float (src/viscositysolver.cpp:379-380)
+    float invdx = 1.0f / g.dx;
+    float factor = dt * invdx * invdx;
+    long long n1 = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
+    FLIP_LAUNCH(k_visc_coefs, cdiv(n1, 256), 256, s.stream, g, (const float *)s.viscosity, (const float *)s.vvol, s.vcoef, factor);
+    FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, g, (const float *)s.vvol, (const float *)s.vcoef,
+                (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r);
+    s.kernel_launches += 2;
+    DiagViscosity diag{s.vdiag, g.total};
+    build_block_list<3>(s, diag);
+    CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
+    CGParams P;
+    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count;
+    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q;
+    P.part = s.part; P.st = s.cgst; P.strict = 0;
+    int G = cg_grid(s);
+    const float *vcoef = s.vcoef, *vdiag = s.vdiag;
+    cudaStream_t st = s.stream;
+    int maxit = s.visc_maxit * s.visc_maxit_scale;
+    CGState h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
+        FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity);
+    });
+    // acceptance rule of src/viscositysolver.cpp:676-689
+    bool accept = !h.fail && (h.converged || (h.iter >= maxit && h.resid < s.visc_accept));
+    if (accept) {
+        FLIP_LAUNCH(k_visc_store, cdiv(n1, 256), 256, s.stream, g, (const float *)s.vdiag, (const double *)s.cg_x, s.vel);
+        s.kernel_launches++;
+    }
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaEventRecord(e1, s.stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
+    s.visc_stats.iters = h.iter; s.visc_stats.converged = h.converged; s.visc_stats.resid = h.resid;
+    s.visc_stats.bmax = h.bmax; s.visc_stats.skipped = accept ? 0 : 2; s.visc_stats.unknowns = *s.count_host;
+    s.visc_stats.ms = ms;
+    if (s.verbose) {
+        printf("\tviscosity: %d iterations, max|r| %.3e (tol %.3e), %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,
+               h.tol, accept ? (h.converged ? "converged" : "accepted") : "FAILED", *s.count_host, ms);
+    }
+}

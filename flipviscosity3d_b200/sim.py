@@ -1,0 +1,201 @@
+"""Python host-side mirror of the C ABI: FlipSim wraps one flip_sim handle.
+
+Grids are numpy float32 arrays shaped (depth, height, width) = (k, j, i), x fastest: the
+reference's Array3d layout (src/array3d.h:397-400).  Particles are (n, 6) float32 AoS
+{pos.xyz, vel.xyz} like the reference's FluidParticle (src/fluidsimulation.h:39-48).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# field ids (include/flip_b200.h)
+F_LIQUID_SDF, F_SOLID_SDF = 0, 1
+F_U, F_V, F_W = 2, 3, 4
+F_SAVED_U, F_SAVED_V, F_SAVED_W = 5, 6, 7
+F_WEIGHT_U, F_WEIGHT_V, F_WEIGHT_W = 8, 9, 10
+F_PRESSURE, F_VISCOSITY = 11, 12
+F_VOL_CENTER, F_VOL_U, F_VOL_V, F_VOL_W, F_VOL_EDGE_U, F_VOL_EDGE_V, F_VOL_EDGE_W = 13, 14, 15, 16, 17, 18, 19
+
+
+class FlipError(RuntimeError):
+    pass
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class FlipSim:
+    def __init__(self, ni, nj, nk, dx, lib=None):
+        self.lib = lib or _lib.default_library()
+        self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        self.dx = float(np.float32(dx))
+        h = C.c_void_p()
+        rc = self.lib.flip_create(self.ni, self.nj, self.nk, C.c_float(dx), C.byref(h))
+        if rc != 0:
+            raise FlipError("flip_create failed (%d): %s" % (rc, (self.lib.flip_last_error(None) or b"").decode()))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.flip_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise FlipError("flip_b200 error %d: %s" % (rc, (self.lib.flip_last_error(self.h) or b"").decode()))
+
+    # ---- shapes ----
+    def field_shape(self, f):
+        ni, nj, nk = self.ni, self.nj, self.nk
+        cells, nodes = (nk, nj, ni), (nk + 1, nj + 1, ni + 1)
+        u, v, w = (nk, nj, ni + 1), (nk, nj + 1, ni), (nk + 1, nj, ni)
+        return {F_LIQUID_SDF: cells, F_SOLID_SDF: nodes, F_U: u, F_V: v, F_W: w, F_SAVED_U: u, F_SAVED_V: v,
+                F_SAVED_W: w, F_WEIGHT_U: u, F_WEIGHT_V: v, F_WEIGHT_W: w, F_PRESSURE: cells, F_VISCOSITY: nodes,
+                F_VOL_CENTER: cells, F_VOL_U: u, F_VOL_V: v, F_VOL_W: w, F_VOL_EDGE_U: (nk + 1, nj + 1, ni),
+                F_VOL_EDGE_V: (nk + 1, nj, ni + 1), F_VOL_EDGE_W: (nk, nj + 1, ni + 1)}[f]
+
+    # ---- scene ----
+    def set_solid_sdf(self, phi):
+        phi = np.ascontiguousarray(phi, np.float32)
+        assert phi.shape == self.field_shape(F_SOLID_SDF)
+        self._ck(self.lib.flip_set_solid_sdf(self.h, _fp(phi)))
+
+    def set_particles(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        assert p.ndim == 2 and p.shape[1] == 6
+        self._ck(self.lib.flip_set_particles(self.h, _fp(p), len(p)))
+
+    def num_particles(self):
+        n = C.c_int64()
+        self._ck(self.lib.flip_num_particles(self.h, C.byref(n)))
+        return n.value
+
+    def get_particles(self, out=None):
+        n = self.num_particles()
+        if out is None:
+            out = np.empty((n, 6), np.float32)
+        m = C.c_int64()
+        self._ck(self.lib.flip_get_particles(self.h, _fp(out), len(out), C.byref(m)))
+        return out[: m.value]
+
+    def set_viscosity(self, v):
+        if np.isscalar(v):
+            self._ck(self.lib.flip_set_viscosity_uniform(self.h, C.c_float(v)))
+        else:
+            v = np.ascontiguousarray(v, np.float32)
+            assert v.shape == self.field_shape(F_VISCOSITY)
+            self._ck(self.lib.flip_set_viscosity_grid(self.h, _fp(v)))
+
+    def set_gravity(self, gx, gy, gz):
+        self._ck(self.lib.flip_set_gravity(self.h, C.c_float(gx), C.c_float(gy), C.c_float(gz)))
+
+    # ---- stepping ----
+    def advance(self, dt):
+        n = C.c_int()
+        self._ck(self.lib.flip_advance(self.h, C.c_float(dt), C.byref(n)))
+        return n.value
+
+    def substep(self, dt):
+        self._ck(self.lib.flip_substep(self.h, C.c_float(dt)))
+
+    def cfl(self):
+        v = C.c_float()
+        self._ck(self.lib.flip_cfl(self.h, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._ck(self.lib.flip_synchronize(self.h))
+
+    # ---- stages ----
+    def update_liquid_sdf(self):
+        self._ck(self.lib.flip_stage_update_liquid_sdf(self.h))
+
+    def advect_velocity_field(self):
+        self._ck(self.lib.flip_stage_advect_velocity_field(self.h))
+
+    def add_body_force(self, dt):
+        self._ck(self.lib.flip_stage_add_body_force(self.h, C.c_float(dt)))
+
+    def apply_viscosity(self, dt):
+        self._ck(self.lib.flip_stage_apply_viscosity(self.h, C.c_float(dt)))
+
+    def project(self, dt):
+        self._ck(self.lib.flip_stage_project(self.h, C.c_float(dt)))
+
+    def constrain(self):
+        self._ck(self.lib.flip_stage_constrain(self.h))
+
+    def advect_particles(self, dt):
+        self._ck(self.lib.flip_stage_advect_particles(self.h, C.c_float(dt)))
+
+    def solve_pressure(self, dt):
+        self._ck(self.lib.flip_solve_pressure(self.h, C.c_float(dt)))
+
+    def apply_pressure(self, dt):
+        self._ck(self.lib.flip_apply_pressure(self.h, C.c_float(dt)))
+
+    def extrapolate(self):
+        self._ck(self.lib.flip_extrapolate(self.h))
+
+    def viscosity_volumes(self):
+        self._ck(self.lib.flip_viscosity_volumes(self.h))
+
+    # ---- fields ----
+    def get_field(self, f):
+        out = np.empty(self.field_shape(f), np.float32)
+        self._ck(self.lib.flip_get_field(self.h, f, _fp(out)))
+        return out
+
+    def set_field(self, f, a):
+        a = np.ascontiguousarray(a, np.float32)
+        assert a.shape == self.field_shape(f), (a.shape, self.field_shape(f))
+        self._ck(self.lib.flip_set_field(self.h, f, _fp(a)))
+
+    def get_mac(self):
+        return self.get_field(F_U), self.get_field(F_V), self.get_field(F_W)
+
+    def set_mac(self, u, v, w):
+        self.set_field(F_U, u); self.set_field(F_V, v); self.set_field(F_W, w)
+
+    def get_saved_mac(self):
+        return self.get_field(F_SAVED_U), self.get_field(F_SAVED_V), self.get_field(F_SAVED_W)
+
+    def set_saved_mac(self, u, v, w):
+        self.set_field(F_SAVED_U, u); self.set_field(F_SAVED_V, v); self.set_field(F_SAVED_W, w)
+
+    def get_weights(self):
+        return self.get_field(F_WEIGHT_U), self.get_field(F_WEIGHT_V), self.get_field(F_WEIGHT_W)
+
+    def get_valid(self):
+        outs = []
+        for c, f in enumerate((F_U, F_V, F_W)):
+            o = np.empty(self.field_shape(f), np.uint8)
+            self._ck(self.lib.flip_get_valid(self.h, c, o.ctypes.data_as(C.POINTER(C.c_uint8))))
+            outs.append(o)
+        return tuple(outs)
+
+    def set_valid(self, u, v, w):
+        for c, (f, a) in enumerate(zip((F_U, F_V, F_W), (u, v, w))):
+            a = np.ascontiguousarray(a, np.uint8)
+            assert a.shape == self.field_shape(f)
+            self._ck(self.lib.flip_set_valid(self.h, c, a.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    # ---- params / stats ----
+    def set_param(self, name, value):
+        self._ck(self.lib.flip_set_param(self.h, name.encode(), C.c_double(value)))
+
+    def stats(self):
+        st = _lib.flip_stats()
+        self._ck(self.lib.flip_get_stats(self.h, C.byref(st)))
+        d = {k: getattr(st, k) for k, _ in st._fields_ if k != "stage_ms"}
+        d["stage_ms"] = list(st.stage_ms)
+        return d
