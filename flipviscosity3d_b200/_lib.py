@@ -22,6 +22,7 @@ class flip_stats(C.Structure):
         ("pressure_rhs_max", C.c_double), ("viscosity_rhs_max", C.c_double),
         ("stage_ms", C.c_float * 8),
         ("pressure_solve_ms", C.c_float), ("viscosity_solve_ms", C.c_float),
+        ("pressure_unknowns", C.c_int64), ("viscosity_unknowns", C.c_int64),
     ]
 
 

@@ -63,10 +63,11 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s.blk_flag, (size_t)g.nblocks);
     dev_alloc(s.blk_list, (size_t)g.nblocks);
     dev_alloc(s.blk_count, 1);
+    dev_alloc(s.unk_count, 1);
     dev_alloc(s.part, 4 * (size_t)FLIP_CG_MAXGRID);
     dev_alloc(s.cgst, 2);
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
-    CUDA_CHECK(cudaMallocHost((void **)&s.count_host, sizeof(int)));
+    CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
     *s.count_host = 0;
     *s.maxvel_host = 0;
@@ -103,7 +104,7 @@ void sim_free(Sim &s) {
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
                     s.weight, s.valid, s.layer, s.fstate, s.viscosity, s.pressure, s.maxvel_dev, s.pcoef, s.cg_x,
                     s.cg_r, s.cg_s, s.cg_q, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
-                    s.blk_count, s.part, s.cgst};
+                    s.blk_count, s.unk_count, s.part, s.cgst};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
     if (s.count_host) cudaFreeHost(s.count_host);
@@ -535,10 +536,12 @@ int flip_get_stats(flip_sim *h, flip_stats *out) {
     out->kernel_launches = s.kernel_launches;
     out->pressure_iterations = s.pres_stats.iters;
     out->pressure_converged = s.pres_stats.converged;
-    out->pressure_active_blocks = s.pres_stats.unknowns;
+    out->pressure_active_blocks = s.pres_stats.blocks;
+    out->pressure_unknowns = s.pres_stats.unknowns;
     out->viscosity_iterations = s.visc_stats.iters;
     out->viscosity_converged = s.visc_stats.converged;
-    out->viscosity_active_blocks = s.visc_stats.unknowns;
+    out->viscosity_active_blocks = s.visc_stats.blocks;
+    out->viscosity_unknowns = s.visc_stats.unknowns;
     out->viscosity_applied = s.visc_stats.skipped == 0 ? 1 : 0;
     out->pressure_residual = s.pres_stats.resid;
     out->viscosity_residual = s.visc_stats.resid;

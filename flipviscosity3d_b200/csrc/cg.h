@@ -271,6 +271,22 @@ static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__res
     if (threadIdx.x == 0) *count = carry_s;
 }
 
+// number of unknowns = non-zero diagonals on the active blocks (integer atomics: exact)
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_count_unknowns(Grid g, const int *__restrict__ list,
+                                                                const int *__restrict__ count, Diag diag, int *__restrict__ out) {
+    int nb = *count;
+    int mine = 0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) mine += diag(m, id) != 0.0f ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 static inline int cg_grid(const Sim &s) {
     int gsz = s.num_sms * 2;
     return gsz > FLIP_CG_MAXGRID ? FLIP_CG_MAXGRID : gsz;
@@ -282,7 +298,10 @@ static void build_block_list(Sim &s, Diag diag) {
     auto kflag = &k_flag_blocks<NC, Diag>;
     FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag);
     FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count);
-    s.kernel_launches += 2;
+    auto kcount = &k_count_unknowns<NC, Diag>;
+    CUDA_CHECK(cudaMemsetAsync(s.unk_count, 0, sizeof(int), s.stream));
+    FLIP_LAUNCH_SYNC(kcount, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.unk_count);
+    s.kernel_launches += 3;
     KERNEL_CHECK();
 }
 

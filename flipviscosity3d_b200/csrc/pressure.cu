@@ -135,13 +135,14 @@ void solve_pressure(Sim &s, float dt) {
     s.kernel_launches++;
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
     CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
     s.pres_stats.iters = h.iter; s.pres_stats.converged = h.converged; s.pres_stats.resid = h.resid;
     s.pres_stats.bmax = h.bmax; s.pres_stats.skipped = (h.iter == 0 && h.converged) ? 1 : 0;
-    s.pres_stats.unknowns = *s.count_host;  // active blocks (the unknown count is not materialised)
+    s.pres_stats.blocks = s.count_host[0]; s.pres_stats.unknowns = s.count_host[1];
     s.pres_stats.ms = ms;
     if (s.verbose) {
         printf("\tpressure: %d iterations, max|r| %.3e, %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,

@@ -18,7 +18,7 @@ struct CGState {
 };
 
 struct SolveStats {
-    int iters; int converged; int unknowns; int skipped; double resid; double bmax; float ms;
+    int iters; int converged; int unknowns; int skipped; double resid; double bmax; float ms; int blocks;
 };
 
 #define FLIP_CG_MAXGRID 1024  // upper bound on the persistent CG grid (partials per reduction)
@@ -87,11 +87,12 @@ struct Sim {
     double *part = 0;         // [4*FLIP_CG_MAXGRID] reduction partials
     CGState *cgst = 0;        // [2] ping-pong
     CGState *cgst_host = 0;   // pinned
-    int *count_host = 0;      // pinned
+    int *count_host = 0;      // pinned [2]: active blocks, unknowns
+    int *unk_count = 0;       // [1] device
 
     // stats of the last substep
-    SolveStats pres_stats = {0, 0, 0, 0, 0, 0, 0};
-    SolveStats visc_stats = {0, 0, 0, 0, 0, 0, 0};
+    SolveStats pres_stats = {0, 0, 0, 0, 0, 0, 0, 0};
+    SolveStats visc_stats = {0, 0, 0, 0, 0, 0, 0, 0};
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long substeps = 0;
     long long kernel_launches = 0;

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_visc_store(Grid g, const float *__restr
 }
 
 void stage_apply_viscosity(Sim &s, float dt) {
-    s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0};
+    s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0, 0};
     if (!s.viscosity_nonzero) return;  // src/fluidsimulation.cpp:171-184
     const Grid &g = s.g;
     cudaEvent_t e0, e1;
@@ -336,12 +336,13 @@ void stage_apply_viscosity(Sim &s, float dt) {
     }
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
     CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
     s.visc_stats.iters = h.iter; s.visc_stats.converged = h.converged; s.visc_stats.resid = h.resid;
-    s.visc_stats.bmax = h.bmax; s.visc_stats.skipped = accept ? 0 : 2; s.visc_stats.unknowns = *s.count_host;
+    s.visc_stats.bmax = h.bmax; s.visc_stats.skipped = accept ? 0 : 2; s.visc_stats.blocks = s.count_host[0]; s.visc_stats.unknowns = s.count_host[1];
     s.visc_stats.ms = ms;
     if (s.verbose) {
         printf("\tviscosity: %d iterations, max|r| %.3e (tol %.3e), %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,

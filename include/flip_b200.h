@@ -73,6 +73,8 @@ typedef struct flip_stats {
     float stage_ms[8];
     float pressure_solve_ms;
     float viscosity_solve_ms;
+    int64_t pressure_unknowns;   /* rows of the last pressure system */
+    int64_t viscosity_unknowns;  /* rows (U+V+W faces) of the last viscosity system */
 } flip_stats;
 
 /* ---- lifetime: FluidSimulation::initialize (src/fluidsimulation.cpp:26-43).  The domain-box
