@@ -55,6 +55,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s.cg_r, 3 * T);
     dev_alloc(s.cg_s, 3 * T);
     dev_alloc(s.cg_q, 3 * T);
+    dev_alloc(s.cg_z, 3 * T);
     dev_alloc(s.vvol, 7 * T);
     dev_alloc(s.vnode, 7 * T);
     dev_alloc(s.vvalid, T);
@@ -100,10 +101,11 @@ void sim_reserve_particles(Sim &s, long long n) {
 
 void sim_free(Sim &s) {
     cudaStreamSynchronize(s.stream);
+    viscosity_free(s);
     free_particles(s);
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
                     s.weight, s.valid, s.layer, s.fstate, s.viscosity, s.pressure, s.maxvel_dev, s.pcoef, s.cg_x,
-                    s.cg_r, s.cg_s, s.cg_q, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
+                    s.cg_r, s.cg_s, s.cg_q, s.cg_z, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
                     s.blk_count, s.unk_count, s.part, s.cgst};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
@@ -520,6 +522,13 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "viscosity_accept") s.visc_accept = value;
     else if (n == "maxit_scale") { s.pressure_maxit_scale = (int)value; s.visc_maxit_scale = (int)value; }
     else if (n == "cg_chunk") s.cg_chunk = (int)value;
+    else if (n == "viscosity_precond") s.visc_precond = (int)value;
+    else if (n == "mg_sweeps") s.mg_sweeps = (int)value;
+    else if (n == "mg_coarse_sweeps") s.mg_coarse_sweeps = (int)value;
+    else if (n == "mg_omega") s.mg_omega = (float)value;
+    else if (n == "mg_alpha") s.mg_alpha = (float)value;
+    else if (n == "mg_minvol") s.mg_minvol = (float)value;
+    else if (n == "mg_levels") s.mg_levels = (int)value;
     else if (n == "pic_ratio") s.pic_ratio = (float)value;
     else if (n == "cfl") { s.cfl_number = (float)value; s.extrap_layers = (int)ceil(s.cfl_number) + 2; }
     else if (n == "verbose") s.verbose = (int)value;

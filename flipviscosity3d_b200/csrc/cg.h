@@ -59,6 +59,7 @@ struct CGParams {
     const int *blk_list;
     const int *blk_count;
     double *x, *r, *s, *q;     // [NC*total]
+    double *z;                 // preconditioned residual (multigrid mode), or null for the diagonal
     double *part;              // [3*gridDim]: s.q | r.z | max|r|
     CGState *st;               // [2]
     int strict;                // 1: converged when max|r| < tol (pressure), 0: <= tol (viscosity)
@@ -130,7 +131,7 @@ static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int 
 }
 
 // phase B: alpha = rho / s.q;  x += alpha s;  r -= alpha q;  partials of r.(M^-1 r) and max|r|
-template <int NC, class Diag>
+template <int NC, class Diag, bool MG>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     const CGState st = P.st[parity];
@@ -152,20 +153,80 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag,
             P.x[o] += alpha * s;
             double r = P.r[o] - alpha * q;
             P.r[o] = r;
-            rz += r * (r / (double)d);
+            if (!MG) rz += r * (r / (double)d);
             rm = fmax(rm, fabs(r));
         }
     }
     rz = cta_reduce<false>(rz, sm);
     rm = cta_reduce<true>(rm, sm);
     if (threadIdx.x == 0) {
-        P.part[gridDim.x + blockIdx.x] = rz;
+        if (!MG) P.part[gridDim.x + blockIdx.x] = rz;
         P.part[2 * gridDim.x + blockIdx.x] = rm;
     }
 }
 
-// phase C: convergence bookkeeping into the other CGState slot, then s = M^-1 r + beta s
+// multigrid mode: partials of r.z after the V-cycle
 template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (parity >= 0 && P.st[parity].done) return;
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    double rz = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            if (diag(m, id) == 0.0f) continue;
+            size_t o = (size_t)m * g.total + id;
+            rz += P.r[o] * P.z[o];
+        }
+    }
+    rz = cta_reduce<false>(rz, sm);
+    if (threadIdx.x == 0) P.part[gridDim.x + blockIdx.x] = rz;
+}
+
+// multigrid mode, start-up: x = 0, r = masked b, partial max|b|   (then V-cycle, k_cg_dot, k_cg_start)
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag) {
+    __shared__ double sm[CG_THREADS / 32];
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    double bm = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            double r = diag(m, id) != 0.0f ? P.r[o] : 0.0;
+            P.r[o] = r;
+            P.x[o] = 0.0;
+            bm = fmax(bm, fabs(r));
+        }
+    }
+    bm = cta_reduce<true>(bm, sm);
+    if (threadIdx.x == 0) P.part[2 * gridDim.x + blockIdx.x] = bm;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_start_mg(CGParams P) {
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            P.s[o] = P.z[o];
+        }
+    }
+}
+
+// phase C: convergence bookkeeping into the other CGState slot, then s = M^-1 r + beta s
+template <int NC, class Diag, bool MG>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag diag, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     const CGState st = P.st[parity];
@@ -177,7 +238,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
     double rho_new = reduce_partials<false>(P.part + gridDim.x, gridDim.x, sm);
     double rmax = reduce_partials<true>(P.part + 2 * gridDim.x, gridDim.x, sm);
     bool conv = P.strict ? (rmax < st.tol) : (rmax <= st.tol);
-    bool bad = rmax != rmax;
+    bool bad = !(rmax == rmax) || !(rho_new == rho_new);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         CGState nx = st;
         nx.iter = st.iter + 1;
@@ -199,7 +260,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
             float d = diag(m, id);
             if (d == 0.0f) continue;
             size_t o = (size_t)m * g.total + id;
-            P.s[o] = P.r[o] / (double)d + beta * P.s[o];
+            P.s[o] = (MG ? P.z[o] : P.r[o] / (double)d) + beta * P.s[o];
         }
     }
 }
@@ -293,6 +354,15 @@ static inline int cg_grid(const Sim &s) {
 }
 
 template <int NC, class Diag>
+static void build_block_list_on(Sim &s, const Grid &g, Diag diag, int *flag, int *list, int *count) {
+    auto kflag = &k_flag_blocks<NC, Diag>;
+    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, flag);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)flag, g.nblocks, list, count);
+    s.kernel_launches += 2;
+    KERNEL_CHECK();
+}
+
+template <int NC, class Diag>
 static void build_block_list(Sim &s, Diag diag) {
     const Grid &g = s.g;
     auto kflag = &k_flag_blocks<NC, Diag>;
@@ -310,8 +380,8 @@ template <int NC, class Diag, class ApplyFn>
 static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply) {
     int G = cg_grid(s);
     auto kinit = &k_cg_init<NC, Diag>;
-    auto kupdate = &k_cg_update<NC, Diag>;
-    auto kdir = &k_cg_direction<NC, Diag>;
+    auto kupdate = &k_cg_update<NC, Diag, false>;
+    auto kdir = &k_cg_direction<NC, Diag, false>;
     FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
     FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
     s.kernel_launches += 2;
@@ -330,6 +400,47 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
             FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
             s.kernel_launches += 3;
+        }
+        KERNEL_CHECK();
+        launched += chunk;
+    }
+    return h;
+}
+
+// Same driver with a general preconditioner: `precond(st)` launches kernels that compute
+// P.z = M^-1 P.r on the active blocks (st = CGState slot to test for `done`, or null at start-up).
+template <int NC, class Diag, class ApplyFn, class PrecondFn>
+static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply,
+                         PrecondFn precond) {
+    int G = cg_grid(s);
+    auto kinit = &k_cg_init_mg<NC, Diag>;
+    auto kstart = &k_cg_start_mg<NC>;
+    auto kdot = &k_cg_dot<NC, Diag>;
+    auto kupdate = &k_cg_update<NC, Diag, true>;
+    auto kdir = &k_cg_direction<NC, Diag, true>;
+    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    precond((const CGState *)nullptr);
+    FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, -1);
+    FLIP_LAUNCH(kstart, G, CG_THREADS, s.stream, P);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
+    s.kernel_launches += 4;
+    KERNEL_CHECK();
+    int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
+    CGState h;
+    int launched = 0;
+    while (true) {
+        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h = *s.cgst_host;
+        if (h.done || launched >= maxit + chunk) break;
+        for (int it = 0; it < chunk; it++) {
+            int parity = it & 1;
+            apply(parity);
+            FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
+            precond((const CGState *)(P.st + parity));
+            FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, parity);
+            FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
+            s.kernel_launches += 4;
         }
         KERNEL_CHECK();
         launched += chunk;

@@ -122,7 +122,7 @@ void solve_pressure(Sim &s, float dt) {
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * (size_t)g.total, s.stream));
     CGParams P;
     P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count;
-    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q;
+    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
     P.part = s.part; P.st = s.cgst; P.strict = 1;
     int G = cg_grid(s);
     const float4 *coef = s.pcoef;

@@ -43,6 +43,13 @@ struct Sim {
     double visc_accept = 10.0;          // src/viscositysolver.h:201
     int visc_maxit = 700;               // src/viscositysolver.h:202
     int visc_maxit_scale = 40;
+    int visc_precond = 0;               // 0 = diagonal (default), 1 = multigrid V-cycle (vmg.h, experimental)
+    int mg_sweeps = 2;                  // damped-Jacobi sweeps before = after the coarse correction
+    int mg_coarse_sweeps = 24;
+    float mg_omega = 0.5f;
+    float mg_minvol = 0.02f;            // coarse faces need at least this liquid volume fraction
+    float mg_alpha = 1.0f;              // scale of the coarse-grid correction
+    int mg_levels = 8;                  // cap on the number of levels
     int cg_chunk = 16;                  // CG iterations launched between host convergence polls
     int verbose = 0;
     bool viscosity_nonzero = true;      // reference initial viscosity is 1.0 everywhere
@@ -76,6 +83,8 @@ struct Sim {
     // --- solver workspaces ---
     float4 *pcoef = 0;        // pressure stencil {diag, +i, +j, +k}
     double *cg_x = 0, *cg_r = 0, *cg_s = 0, *cg_q = 0;   // [3*total] (pressure uses component 0)
+    double *cg_z = 0;         // [3*total] preconditioned residual (multigrid mode)
+    void *vmg = 0;            // viscosity multigrid hierarchy (VMG*, viscosity.cu)
     float *vvol = 0;          // 7 volume grids [7*total]: center,U,V,W,edgeU,edgeV,edgeW
     float *vnode = 0;         // 7 nodal phi grids [7*total]
     unsigned char *vvalid = 0;// dilated liquid mask
@@ -124,6 +133,7 @@ void stage_project(Sim &s, float dt);
 void solve_pressure(Sim &s, float dt);
 void stage_apply_viscosity(Sim &s, float dt);
 void viscosity_volumes(Sim &s);
+void viscosity_free(Sim &s);
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);
