@@ -150,7 +150,7 @@ def run_reference(args):
 def workload_config(args, particles):
     return {"workload": "bunny_in_sphere_%d^3_8ppc_viscosity%g (BASELINE.json configs[3])" % (args.size, args.viscosity),
             "grid": [args.size] * 3, "particles": int(particles), "viscosity": args.viscosity, "frame_dt": FRAME_DT,
-            "step": "one substep of FluidSimulation::advance", "parallelism": "k-slab x%d" % args.gpus,
+            "step": "one substep of FluidSimulation::advance", "parallelism": "k-slab CG x%d (particle/grid stages replicated)" % args.gpus,
             "l2": "working set (fields + CG vectors of the active blocks) exceeds the 126 MB L2; no flush between steps"}
 
 
@@ -179,7 +179,10 @@ def run_b200(args):
     sim.set_particles(p)
     sim.set_viscosity(visc)
     if world > 1:
-        raise SystemExit("multi-GPU path not wired into bench.py yet")
+        # NCCL communicator of the library: rank 0 makes the unique id, torch.distributed ships it
+        box = [sim.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sim.dist_init(rank, world, box[0])
 
     def barrier_sync():
         if world > 1:

@@ -72,6 +72,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
     *s.count_host = 0;
     *s.maxvel_host = 0;
+    dist_setup_slab(s);
     // initial solid: none (phi = +large everywhere) until flip_set_solid_sdf; viscosity 1.0
     // like the reference's initialize (src/fluidsimulation.cpp:39)
 }
@@ -101,6 +102,7 @@ void sim_reserve_particles(Sim &s, long long n) {
 
 void sim_free(Sim &s) {
     cudaStreamSynchronize(s.stream);
+    try { dist_shutdown(s); } catch (...) {}
     viscosity_free(s);
     free_particles(s);
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
@@ -559,6 +561,20 @@ int flip_get_stats(flip_sim *h, flip_stats *out) {
     for (int i = 0; i < 8; i++) out->stage_ms[i] = s.stage_ms[i];
     out->pressure_solve_ms = s.pres_stats.ms;
     out->viscosity_solve_ms = s.visc_stats.ms;
+    return FLIP_OK;
+}
+
+int flip_dist_unique_id(void *out128) {
+    if (!out128) return FLIP_EINVAL;
+    try { dist_get_unique_id(out128); } catch (const std::exception &e) { g_create_error = e.what(); return FLIP_ENCCL; }
+    return FLIP_OK;
+}
+
+int flip_dist_init(flip_sim *h, int rank, int nranks, const void *unique_id128) {
+    if (!h) return FLIP_EINVAL;
+    Sim &s = h->s;
+    if (nranks > 1 && !unique_id128) return fail_inval(s, "flip_dist_init: unique id required");
+    try { dist_init(s, rank, nranks, unique_id128); } catch (const std::exception &e) { s.last_error = e.what(); return FLIP_ENCCL; }
     return FLIP_OK;
 }
 

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_flag_blocks(Grid g, Diag diag, i
 
 // single CTA, ordered compaction (ascending block id => deterministic CTA/block assignment)
 static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__restrict__ flag, int n, int *__restrict__ list,
-                                                         int *__restrict__ count) {
+                                                         int *__restrict__ count, int lo, int hi) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
@@ -306,7 +306,7 @@ static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__res
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int base = 0; base < n; base += 1024) {
         int id = base + threadIdx.x;
-        int v = (id < n && flag[id]) ? 1 : 0;
+        int v = (id < n && id >= lo && id < hi && flag[id]) ? 1 : 0;   // [lo,hi): this rank's slab of blocks
         int inc = v;
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -357,7 +357,7 @@ template <int NC, class Diag>
 static void build_block_list_on(Sim &s, const Grid &g, Diag diag, int *flag, int *list, int *count) {
     auto kflag = &k_flag_blocks<NC, Diag>;
     FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, flag);
-    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)flag, g.nblocks, list, count);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)flag, g.nblocks, list, count, 0, g.nblocks);
     s.kernel_launches += 2;
     KERNEL_CHECK();
 }
@@ -367,10 +367,12 @@ static void build_block_list(Sim &s, Diag diag) {
     const Grid &g = s.g;
     auto kflag = &k_flag_blocks<NC, Diag>;
     FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag);
-    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count,
+                     s.bz0 * g.nbx * g.nby, s.bz1 * g.nbx * g.nby);
     auto kcount = &k_count_unknowns<NC, Diag>;
     CUDA_CHECK(cudaMemsetAsync(s.unk_count, 0, sizeof(int), s.stream));
     FLIP_LAUNCH_SYNC(kcount, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.unk_count);
+    dist_allreduce_int(s, s.unk_count);
     s.kernel_launches += 3;
     KERNEL_CHECK();
 }
@@ -383,6 +385,8 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
     auto kupdate = &k_cg_update<NC, Diag, false>;
     auto kdir = &k_cg_direction<NC, Diag, false>;
     FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    dist_reduce_partials(s, P.part + G, G, false);
+    dist_reduce_partials(s, P.part + 2 * G, G, true);
     FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
     s.kernel_launches += 2;
     KERNEL_CHECK();
@@ -397,7 +401,10 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;
             apply(parity);
+            dist_reduce_partials(s, P.part, G, false);
             FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
+            dist_reduce_partials(s, P.part + G, G, false);
+            dist_reduce_partials(s, P.part + 2 * G, G, true);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
             s.kernel_launches += 3;
         }

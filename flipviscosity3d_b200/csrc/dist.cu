@@ -1,0 +1,146 @@
+// Multi-GPU support: one process per GPU, 1-D slab decomposition along k (the slowest index, so a
+// slab and its ghost planes are contiguous in memory), NCCL over NVLink for the exchanges.
+//
+// What is decomposed: the two CG solves, which are > 90 % of a substep — each rank applies the
+// stencil and the vector updates on its own slab of 8x8x8 blocks, exchanges ONE ghost plane of the
+// search direction with each k-neighbour per stencil apply (three planes, U/V/W, for the viscosity
+// system) and all-reduces the CG scalars.  What is replicated: the particle and grid stages
+// (binning, SDF, P2G, extrapolation, G2P; ~2 % of a 256^3 substep) run identically on every rank —
+// they are deterministic, so the replicas stay bit-identical — and each solve ends with an
+// all-gather of the solution slabs.  SURVEY.md §8(e) describes the fully partitioned variant
+// (particle migration, halo-min/halo-add); that is the next step, see DESIGN.md.
+//
+// The reference has no multi-process path at all, so nothing here replaces
+// reference code.
+#include "sim.h"
+
+#ifdef FLIP_CPU_EMU
+// the CPU emulator is single-process
+void dist_setup_slab(Sim &s) { s.bz0 = 0; s.bz1 = s.g.nbz; }
+void dist_init(Sim &, int, int nranks, const void *) { if (nranks != 1) throw FlipError("cpu-emu build is single process"); }
+void dist_shutdown(Sim &) {}
+void dist_get_unique_id(void *out128) { memset(out128, 0, 128); }
+void dist_reduce_partials(Sim &, double *, int, bool) {}
+void dist_halo_exchange(Sim &, double *, int) {}
+void dist_allgather_slabs(Sim &, double *, int) {}
+void dist_allreduce_int(Sim &, int *) {}
+#else
+#include <nccl.h>
+#include <cstring>
+
+#define NCCL_CHECK(expr)                                                                          \
+    do {                                                                                          \
+        ncclResult_t _r = (expr);                                                                 \
+        if (_r != ncclSuccess)                                                                    \
+            throw FlipError(std::string(#expr) + " failed: " + ncclGetErrorString(_r));           \
+    } while (0)
+
+void dist_setup_slab(Sim &s) {
+    int nbz = s.g.nbz;
+    s.bz0 = (int)((long long)nbz * s.rank / s.nranks);
+    s.bz1 = (int)((long long)nbz * (s.rank + 1) / s.nranks);
+}
+
+void dist_get_unique_id(void *out128) {
+    ncclUniqueId id;
+    NCCL_CHECK(ncclGetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+}
+
+void dist_init(Sim &s, int rank, int nranks, const void *unique_id) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw FlipError("dist_init: bad rank / nranks");
+    if (nranks > s.g.nbz) throw FlipError("dist_init: more ranks than 8-cell block layers along k");
+    dist_shutdown(s);
+    s.rank = rank; s.nranks = nranks;
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, unique_id, 128);
+        ncclComm_t comm;
+        NCCL_CHECK(ncclCommInitRank(&comm, nranks, id, rank));
+        s.nccl = (void *)comm;
+    }
+    dist_setup_slab(s);
+}
+
+void dist_shutdown(Sim &s) {
+    if (s.nccl) { ncclCommDestroy((ncclComm_t)s.nccl); s.nccl = 0; }
+    s.rank = 0; s.nranks = 1;
+    dist_setup_slab(s);
+}
+
+// part[0] = reduce(part[0..n)), part[1..n) = 0: consumers that re-reduce the n partials then see the
+// global value once the all-reduce has run on part[0]
+__global__ void __launch_bounds__(512) k_collapse_partials(double *__restrict__ part, int n, int is_max) {
+    __shared__ double sm[16];
+    double v = 0.0;
+    for (int q = threadIdx.x; q < n; q += 512) v = is_max ? fmax(v, part[q]) : v + part[q];
+    for (int o = 16; o > 0; o >>= 1) {
+        double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, u) : v + u;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+    for (int w = 1; w < 16; w++) r = is_max ? fmax(r, sm[w]) : r + sm[w];
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += 512) part[q] = (q == 0) ? r : 0.0;
+}
+
+void dist_reduce_partials(Sim &s, double *part, int n, bool is_max) {
+    if (s.nranks == 1) return;
+    k_collapse_partials<<<1, 512, 0, s.stream>>>(part, n, is_max ? 1 : 0);
+    s.kernel_launches++;
+    NCCL_CHECK(ncclAllReduce(part, part, 1, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)s.nccl, s.stream));
+}
+
+void dist_allreduce_int(Sim &s, int *dev_value) {
+    if (s.nranks == 1) return;
+    NCCL_CHECK(ncclAllReduce(dev_value, dev_value, 1, ncclInt, ncclSum, (ncclComm_t)s.nccl, s.stream));
+}
+
+static inline size_t plane_elems(const Grid &g) { return (size_t)g.ax * g.ay; }
+static inline size_t plane_offset(const Grid &g, int k) { return (size_t)(k + FLIP_PZ) * plane_elems(g); }
+
+// Owned cell planes of this rank: k in [8*bz0, min(8*bz1, nk+1)).  The plane just below / above the
+// slab is the ghost layer the 7-point and the coupled-face stencils read.
+void dist_halo_exchange(Sim &s, double *field, int ncomp) {
+    if (s.nranks == 1) return;
+    const Grid &g = s.g;
+    ncclComm_t comm = (ncclComm_t)s.nccl;
+    int k0 = FLIP_B * s.bz0, k1 = FLIP_B * s.bz1;   // k1 may exceed nk+1 on the last rank (no upper neighbour then)
+    size_t pe = plane_elems(g);
+    NCCL_CHECK(ncclGroupStart());
+    for (int c = 0; c < ncomp; c++) {
+        double *f = field + (size_t)c * g.total;
+        if (s.rank > 0) {
+            NCCL_CHECK(ncclSend(f + plane_offset(g, k0), pe, ncclDouble, s.rank - 1, comm, s.stream));
+            NCCL_CHECK(ncclRecv(f + plane_offset(g, k0 - 1), pe, ncclDouble, s.rank - 1, comm, s.stream));
+        }
+        if (s.rank < s.nranks - 1) {
+            NCCL_CHECK(ncclSend(f + plane_offset(g, k1 - 1), pe, ncclDouble, s.rank + 1, comm, s.stream));
+            NCCL_CHECK(ncclRecv(f + plane_offset(g, k1), pe, ncclDouble, s.rank + 1, comm, s.stream));
+        }
+    }
+    NCCL_CHECK(ncclGroupEnd());
+}
+
+void dist_allgather_slabs(Sim &s, double *field, int ncomp) {
+    if (s.nranks == 1) return;
+    const Grid &g = s.g;
+    ncclComm_t comm = (ncclComm_t)s.nccl;
+    size_t pe = plane_elems(g);
+    NCCL_CHECK(ncclGroupStart());
+    for (int r = 0; r < s.nranks; r++) {
+        int b0 = (int)((long long)g.nbz * r / s.nranks), b1 = (int)((long long)g.nbz * (r + 1) / s.nranks);
+        int k0 = FLIP_B * b0, k1 = FLIP_B * b1;
+        if (k1 > g.nk + 1) k1 = g.nk + 1;
+        if (k1 <= k0) continue;
+        for (int c = 0; c < ncomp; c++) {
+            double *f = field + (size_t)c * g.total + plane_offset(g, k0);
+            NCCL_CHECK(ncclBroadcast(f, f, (size_t)(k1 - k0) * pe, ncclDouble, r, comm, s.stream));
+        }
+    }
+    NCCL_CHECK(ncclGroupEnd());
+}
+#endif

@@ -99,6 +99,11 @@ struct Sim {
     int *count_host = 0;      // pinned [2]: active blocks, unknowns
     int *unk_count = 0;       // [1] device
 
+    // --- multi-GPU: 1-D slab decomposition of the solver blocks along k (dist.cu) ---
+    int rank = 0, nranks = 1;
+    void *nccl = 0;           // ncclComm_t
+    int bz0 = 0, bz1 = 0;     // owned range of 8-cell block layers in k: [bz0, bz1)
+
     // stats of the last substep
     SolveStats pres_stats = {0, 0, 0, 0, 0, 0, 0, 0};
     SolveStats visc_stats = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -134,6 +139,16 @@ void solve_pressure(Sim &s, float dt);
 void stage_apply_viscosity(Sim &s, float dt);
 void viscosity_volumes(Sim &s);
 void viscosity_free(Sim &s);
+
+// dist.cu
+void dist_setup_slab(Sim &s);
+void dist_init(Sim &s, int rank, int nranks, const void *unique_id);
+void dist_shutdown(Sim &s);
+void dist_get_unique_id(void *out128);
+void dist_reduce_partials(Sim &s, double *part, int n, bool is_max);   // collapse n partials + allreduce
+void dist_halo_exchange(Sim &s, double *field, int ncomp);            // one ghost plane each side of the slab
+void dist_allgather_slabs(Sim &s, double *field, int ncomp);          // every rank gets every slab
+void dist_allreduce_int(Sim &s, int *dev_value);
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);

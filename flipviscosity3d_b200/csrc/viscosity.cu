@@ -475,7 +475,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     cudaStream_t st = s.stream;
     int maxit = s.visc_maxit * s.visc_maxit_scale;
     CGState h;
-    if (s.visc_precond == 1) {
+    if (s.visc_precond == 1 && s.nranks == 1) {
         VMG *M = vmg_get(s);
         vmg_build(s, *M);
         P.z = s.cg_z;
@@ -484,9 +484,11 @@ void stage_apply_viscosity(Sim &s, float dt) {
                          [&](const CGState *cst) { vmg_vcycle(s, *M, (const double *)P.r, P.z, cst); });
     } else {
         h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
+            dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
             FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity);
         });
     }
+    dist_allgather_slabs(s, s.cg_x, 3);
     // acceptance rule of src/viscositysolver.cpp:676-689
     bool accept = !h.fail && (h.converged || (h.iter >= maxit && h.resid < s.visc_accept));
     if (accept) {

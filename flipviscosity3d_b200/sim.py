@@ -189,6 +189,18 @@ class FlipSim:
             assert a.shape == self.field_shape(f)
             self._ck(self.lib.flip_set_valid(self.h, c, a.ctypes.data_as(C.POINTER(C.c_uint8))))
 
+    # ---- multi-GPU ----
+    def dist_unique_id(self):
+        buf = C.create_string_buffer(128)
+        rc = self.lib.flip_dist_unique_id(buf)
+        if rc != 0:
+            raise FlipError("flip_dist_unique_id failed (%d)" % rc)
+        return buf.raw
+
+    def dist_init(self, rank, nranks, unique_id=None):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._ck(self.lib.flip_dist_init(self.h, int(rank), int(nranks), buf))
+
     # ---- params / stats ----
     def set_param(self, name, value):
         self._ck(self.lib.flip_set_param(self.h, name.encode(), C.c_double(value)))

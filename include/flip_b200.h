@@ -135,6 +135,15 @@ int flip_set_valid(flip_sim *h, int comp, const uint8_t *in);
 int flip_set_param(flip_sim *h, const char *name, double value);
 int flip_get_stats(flip_sim *h, flip_stats *out);
 
+/* ---- multi-GPU (no reference counterpart: the reference is single-threaded) ----
+ * One process per GPU.  Rank 0 calls flip_dist_unique_id and ships the 128 bytes to the other
+ * ranks (bench.py uses torch.distributed for that); every rank then calls flip_dist_init on its own
+ * handle.  Every rank must hold the same scene (same solid SDF, particles, parameters) and issue the
+ * same calls: the CG solves are decomposed into k-slabs with NCCL halo exchange and all-reduce, the
+ * particle/grid stages run replicated (multi-GPU). */
+int flip_dist_unique_id(void *out128);
+int flip_dist_init(flip_sim *h, int rank, int nranks, const void *unique_id128);
+
 /* pinned host buffers for callers that want asynchronous copies */
 int flip_host_alloc(void **ptr, uint64_t bytes);
 int flip_host_free(void *ptr);
