@@ -25,8 +25,62 @@ void dist_halo_exchange(Sim &, double *, int) {}
 void dist_allgather_slabs(Sim &, double *, int) {}
 void dist_allreduce_int(Sim &, int *) {}
 #else
-#include <nccl.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
+#include <dlfcn.h>
 #include <cstring>
+
+// NCCL is resolved with dlopen at flip_dist_init time instead of at link time.  A process that
+// also uses PyTorch has torch's bundled libnccl.so.2 (2.28) mapped; linking this library against
+// the system one (2.27) made whichever loaded first win for both, and torch then failed to find its
+// newer symbols.  dlopen("libnccl.so.2") returns the copy that is already mapped, or the system
+// one in a plain C++ host.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi &nccl_api() {
+    static NcclApi api;
+    if (api.handle) return api;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw FlipError(std::string("cannot load libnccl.so.2: ") + dlerror());
+#define FLIP_NCCL_SYM(field, name)                                             \
+    api.field = (decltype(api.field))dlsym(h, name);                           \
+    if (!api.field) throw FlipError(std::string("libnccl lacks ") + name);
+    FLIP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    FLIP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    FLIP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    FLIP_NCCL_SYM(AllReduce, "ncclAllReduce")
+    FLIP_NCCL_SYM(Broadcast, "ncclBroadcast")
+    FLIP_NCCL_SYM(Send, "ncclSend")
+    FLIP_NCCL_SYM(Recv, "ncclRecv")
+    FLIP_NCCL_SYM(GroupStart, "ncclGroupStart")
+    FLIP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    FLIP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef FLIP_NCCL_SYM
+    api.handle = h;
+    return api;
+}
+#define ncclGetUniqueId nccl_api().GetUniqueId
+#define ncclCommInitRank nccl_api().CommInitRank
+#define ncclCommDestroy nccl_api().CommDestroy
+#define ncclAllReduce nccl_api().AllReduce
+#define ncclBroadcast nccl_api().Broadcast
+#define ncclSend nccl_api().Send
+#define ncclRecv nccl_api().Recv
+#define ncclGroupStart nccl_api().GroupStart
+#define ncclGroupEnd nccl_api().GroupEnd
+#define ncclGetErrorString nccl_api().GetErrorString
 
 #define NCCL_CHECK(expr)                                                                          \
     do {                                                                                          \
