@@ -103,6 +103,9 @@ void sim_reserve_particles(Sim &s, long long n) {
 void sim_free(Sim &s) {
     cudaStreamSynchronize(s.stream);
     try { dist_shutdown(s); } catch (...) {}
+#ifndef FLIP_CPU_EMU
+    for (int q = 0; q < 2; q++) if (s.cg_graph[q]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[q]); s.cg_graph[q] = 0; }
+#endif
     viscosity_free(s);
     free_particles(s);
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
@@ -524,12 +527,15 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "viscosity_accept") s.visc_accept = value;
     else if (n == "maxit_scale") { s.pressure_maxit_scale = (int)value; s.visc_maxit_scale = (int)value; }
     else if (n == "cg_chunk") s.cg_chunk = (int)value;
+    else if (n == "use_graphs") s.use_graphs = (int)value;
+    else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
     else if (n == "mg_sweeps") s.mg_sweeps = (int)value;
     else if (n == "mg_coarse_sweeps") s.mg_coarse_sweeps = (int)value;
     else if (n == "mg_omega") s.mg_omega = (float)value;
     else if (n == "mg_alpha") s.mg_alpha = (float)value;
     else if (n == "mg_minvol") s.mg_minvol = (float)value;
+    else if (n == "mg_prune") s.mg_prune = (int)value;
     else if (n == "mg_levels") s.mg_levels = (int)value;
     else if (n == "pic_ratio") s.pic_ratio = (float)value;
     else if (n == "cfl") { s.cfl_number = (float)value; s.extrap_layers = (int)ceil(s.cfl_number) + 2; }

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_count_unknowns(Grid g, const int
 }
 
 static inline int cg_grid(const Sim &s) {
-    int gsz = s.num_sms * 2;
+    int gsz = s.num_sms * s.cg_grid_mult;
     return gsz > FLIP_CG_MAXGRID ? FLIP_CG_MAXGRID : gsz;
 }
 
@@ -378,8 +378,12 @@ static void build_block_list(Sim &s, Diag diag) {
 }
 
 // Generic driver.  `apply(parity)` launches the phase-A kernel (q = A s and the s.q partials).
+// On one GPU a chunk of `cg_chunk` iterations (3 kernels each) is captured ONCE into a CUDA graph
+// per solver (all kernel arguments are pointers into the handle's own buffers and never change) and
+// replayed; convergence is decided on the device, the host only polls the 64-byte state per chunk.
 template <int NC, class Diag, class ApplyFn>
-static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply) {
+static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply,
+                      int graph_slot = -1) {
     int G = cg_grid(s);
     auto kinit = &k_cg_init<NC, Diag>;
     auto kupdate = &k_cg_update<NC, Diag, false>;
@@ -391,13 +395,7 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
     s.kernel_launches += 2;
     KERNEL_CHECK();
     int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
-    CGState h;
-    int launched = 0;
-    while (true) {
-        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        h = *s.cgst_host;
-        if (h.done || launched >= maxit + chunk) break;
+    auto launch_chunk = [&]() {
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;
             apply(parity);
@@ -406,8 +404,38 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
             dist_reduce_partials(s, P.part + G, G, false);
             dist_reduce_partials(s, P.part + 2 * G, G, true);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
-            s.kernel_launches += 3;
         }
+    };
+#ifndef FLIP_CPU_EMU
+    bool use_graph = s.use_graphs && s.nranks == 1 && graph_slot >= 0 && graph_slot < 2;
+    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk)) {
+        if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        launch_chunk();
+        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        s.cg_graph[graph_slot] = (void *)exec;
+        s.cg_graph_chunk[graph_slot] = chunk;
+    }
+#else
+    bool use_graph = false;
+#endif
+    CGState h;
+    int launched = 0;
+    while (true) {
+        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h = *s.cgst_host;
+        if (h.done || launched >= maxit + chunk) break;
+#ifndef FLIP_CPU_EMU
+        if (use_graph) CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream));
+        else
+#endif
+            launch_chunk();
+        s.kernel_launches += 3 * chunk;
         KERNEL_CHECK();
         launched += chunk;
     }

@@ -130,7 +130,7 @@ void solve_pressure(Sim &s, float dt) {
     CGState h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, s.pressure_maxit * s.pressure_maxit_scale, [&](int parity) {
         dist_halo_exchange(s, P.s, 1);   // one ghost plane of the search direction per stencil apply
         FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, P, coef, parity);
-    });
+    }, 0);
     dist_allgather_slabs(s, s.cg_x, 1);
     long long nc = (long long)g.ni * g.nj * g.nk;
     FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);

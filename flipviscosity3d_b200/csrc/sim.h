@@ -48,10 +48,15 @@ struct Sim {
     int mg_coarse_sweeps = 24;
     float mg_omega = 0.5f;
     float mg_minvol = 0.02f;            // coarse faces need at least this liquid volume fraction
+    int mg_prune = 0;                   // 1: drop coarse strain terms that touch air faces (made it worse: off)
     float mg_alpha = 1.0f;              // scale of the coarse-grid correction
     int mg_levels = 8;                  // cap on the number of levels
-    int cg_chunk = 16;                  // CG iterations launched between host convergence polls
+    int cg_chunk = 32;
+    int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
     int verbose = 0;
+    int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph (1 GPU)
+    void *cg_graph[2] = {0, 0};         // cudaGraphExec_t: [0] pressure, [1] viscosity
+    int cg_graph_chunk[2] = {0, 0};
     bool viscosity_nonzero = true;      // reference initial viscosity is 1.0 everywhere
 
     // --- particles (SoA, cell-binned every substep) ---

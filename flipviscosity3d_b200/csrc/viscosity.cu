@@ -308,12 +308,13 @@ static VMG *vmg_get(Sim &s) {
         vmg_dev_alloc(L.x[1], 3 * T);
         vmg_dev_alloc(L.r, 3 * T);
         if (l == 0) {
-            L.coef = s.vcoef; L.diag = s.vdiag; L.vol = s.vvol + T; L.b = nullptr;
+            L.coef = s.vcoef; L.diag = s.vdiag; L.vol = s.vvol + T; L.b = nullptr; L.wall = s.fstate;
             L.blk_flag = s.blk_flag; L.blk_list = s.blk_list; L.blk_count = s.blk_count;
             L.owns = false;
         } else {
             vmg_dev_alloc(L.coef, 4 * T); vmg_dev_alloc(L.diag, 3 * T); vmg_dev_alloc(L.vol, 3 * T);
             vmg_dev_alloc(L.b, 3 * T);
+            vmg_dev_alloc(L.wall, 3 * T);
             vmg_dev_alloc(L.blk_flag, (size_t)g.nblocks); vmg_dev_alloc(L.blk_list, (size_t)g.nblocks);
             vmg_dev_alloc(L.blk_count, 1);
             L.owns = true;
@@ -336,7 +337,7 @@ void viscosity_free(Sim &s) {
         VLevel &L = M->lv[l];
         cudaFree(L.x[0]); cudaFree(L.x[1]); cudaFree(L.r);
         if (L.owns) {
-            cudaFree(L.coef); cudaFree(L.diag); cudaFree(L.vol); cudaFree(L.b);
+            cudaFree(L.coef); cudaFree(L.diag); cudaFree(L.vol); cudaFree(L.b); cudaFree(L.wall);
             cudaFree(L.blk_flag); cudaFree(L.blk_list); cudaFree(L.blk_count);
         }
     }
@@ -374,9 +375,11 @@ static void vmg_build(Sim &s, VMG &M) {
         const VLevel &F = M.lv[l - 1];
         long long n = (long long)(L.g.ni + 1) * (L.g.nj + 1) * (L.g.nk + 1);
         FLIP_LAUNCH(k_vmg_coarsen_coefs, cdiv(n, 256), 256, s.stream, L.g, F.g, (const float *)F.coef, (const float *)F.vol,
-                    (const float *)F.diag, L.coef, L.vol, L.diag);
-        FLIP_LAUNCH(k_vmg_coarsen_rows, cdiv(n, 256), 256, s.stream, L.g, (const float *)L.coef, (const float *)L.vol, L.diag, s.mg_minvol);
-        s.kernel_launches += 2;
+                    (const float *)F.diag, L.coef, L.vol, L.diag, (const unsigned char *)F.wall, L.wall);
+        FLIP_LAUNCH(k_vmg_classify, cdiv(n, 256), 256, s.stream, L.g, (const float *)L.vol, L.diag, L.wall, s.mg_minvol);
+        if (s.mg_prune) FLIP_LAUNCH(k_vmg_prune, cdiv(n, 256), 256, s.stream, L.g, L.coef, (const float *)L.diag, (const unsigned char *)L.wall);
+        FLIP_LAUNCH(k_vmg_coarsen_rows, cdiv(n, 256), 256, s.stream, L.g, (const float *)L.coef, (const float *)L.vol, L.diag);
+        s.kernel_launches += 4;
         DiagViscosity d{L.diag, L.g.total};
         build_block_list_on<3>(s, L.g, d, L.blk_flag, L.blk_list, L.blk_count);
     }
@@ -486,7 +489,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
         h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
             dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
             FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity);
-        });
+        }, 1);
     }
     dist_allgather_slabs(s, s.cg_x, 3);
     // acceptance rule of src/viscositysolver.cpp:676-689

@@ -26,6 +26,7 @@ struct VLevel {
     float *x[2];     // [3T] ping-pong iterate
     float *b;        // [3T] right-hand side
     float *r;        // [3T] residual
+    unsigned char *wall;   // [3T] 1 = solid (Dirichlet) face
     int *blk_flag, *blk_list, *blk_count;
     bool owns;       // level 0 borrows coef/diag/vol/block list from the solver
 };
@@ -298,7 +299,8 @@ FLIP_D float vmg_average(const Grid &gf, const float *__restrict__ f, int I, int
 __global__ void __launch_bounds__(256) k_vmg_coarsen_coefs(Grid gc, Grid gf, const float *__restrict__ coef_f,
                                                            const float *__restrict__ vol_f, const float *__restrict__ diag_f,
                                                            float *__restrict__ coef_c, float *__restrict__ vol_c,
-                                                           float *__restrict__ mask_c) {
+                                                           float *__restrict__ mask_c, const unsigned char *__restrict__ wall_f,
+                                                           unsigned char *__restrict__ wall_c) {
     int I, J, K;
     if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, gc.ni + 1, gc.nj + 1, gc.nk + 1, I, J, K)) return;
     size_t Tf = (size_t)gf.total, Tc = (size_t)gc.total;
@@ -314,30 +316,84 @@ __global__ void __launch_bounds__(256) k_vmg_coarsen_coefs(Grid gc, Grid gf, con
     // a coarse face is an unknown if any fine face it interpolates to is one
     for (int m = 0; m < 3; m++) {
         float any = 0.0f;
+        unsigned char wall = 0;
         for (int a = (m == 0 ? -1 : 0); a <= 1; a++)
             for (int b = (m == 1 ? -1 : 0); b <= 1; b++)
-                for (int c = (m == 2 ? -1 : 0); c <= 1; c++)
-                    if (vmg_fetch(gf, diag_f + m * Tf, 2 * I + a, 2 * J + b, 2 * K + c) != 0.0f) any = 1.0f;
+                for (int c = (m == 2 ? -1 : 0); c <= 1; c++) {
+                    int fi = 2 * I + a, fj = 2 * J + b, fk = 2 * K + c;
+                    if (fi < 0 || fj < 0 || fk < 0 || fi > gf.ni || fj > gf.nj || fk > gf.nk) continue;
+                    int fid = gidx(gf, fi, fj, fk);
+                    if (diag_f[m * Tf + fid] != 0.0f) any = 1.0f;
+                    if (wall_f[m * Tf + fid]) wall = 1;
+                }
         mask_c[m * Tc + id] = any;
+        wall_c[m * Tc + id] = wall;
     }
 }
 
-// coarse row diagonals (mask_c arrives in diag_c and is overwritten)
+// Coarse faces are unknowns if a fine child is and their control volume holds real liquid mass.  A
+// face that is not an unknown is either a wall (some child is solid: Dirichlet, its couplings stay
+// in the neighbours' diagonals) or air.  Strain terms that touch an AIR face are removed from the
+// coarse operator altogether (next kernel) instead of pinning that face to zero: rigid motions of
+// a free-floating body of liquid then keep zero strain energy on every level, as they have on
+// the fine one.
+__global__ void __launch_bounds__(256) k_vmg_classify(Grid gc, const float *__restrict__ vol, float *__restrict__ diag,
+                                                      unsigned char *__restrict__ wall, float minvol) {
+    int I, J, K;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, gc.ni + 1, gc.nj + 1, gc.nk + 1, I, J, K)) return;
+    size_t T = (size_t)gc.total;
+    int id = gidx(gc, I, J, K);
+    bool interior = I >= 1 && I < gc.ni && J >= 1 && J < gc.nj && K >= 1 && K < gc.nk;
+    for (int m = 0; m < 3; m++) {
+        bool unk = interior && diag[m * T + id] != 0.0f && vol[m * T + id] >= minvol;
+        diag[m * T + id] = unk ? 1.0f : 0.0f;
+        // faces on the rim of the index box count as walls (the domain boundary is solid)
+        bool rim = !interior;
+        wall[m * T + id] = (!unk && (wall[m * T + id] || rim)) ? 1 : 0;
+    }
+}
+
+FLIP_D bool vmg_air(const Grid &g, const float *__restrict__ diag, const unsigned char *__restrict__ wall, int m, int i, int j, int k) {
+    if (i < 0 || j < 0 || k < 0 || i > g.ni || j > g.nj || k > g.nk) return false;  // outside: wall
+    size_t o = (size_t)m * g.total + gidx(g, i, j, k);
+    return diag[o] == 0.0f && !wall[o];
+}
+
+__global__ void __launch_bounds__(256) k_vmg_prune(Grid gc, float *__restrict__ coef, const float *__restrict__ diag,
+                                                   const unsigned char *__restrict__ wall) {
+    int I, J, K;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, gc.ni + 1, gc.nj + 1, gc.nk + 1, I, J, K)) return;
+    size_t T = (size_t)gc.total;
+    int id = gidx(gc, I, J, K);
+    // cell term: pairs U(I),U(I+1) / V(J),V(J+1) / W(K),W(K+1)
+    if (vmg_air(gc, diag, wall, 0, I, J, K) || vmg_air(gc, diag, wall, 0, I + 1, J, K) || vmg_air(gc, diag, wall, 1, I, J, K) ||
+        vmg_air(gc, diag, wall, 1, I, J + 1, K) || vmg_air(gc, diag, wall, 2, I, J, K) || vmg_air(gc, diag, wall, 2, I, J, K + 1))
+        coef[id] = 0.0f;
+    // edge along x at node (J,K): V(I,J,K), V(I,J,K-1), W(I,J,K), W(I,J-1,K)
+    if (vmg_air(gc, diag, wall, 1, I, J, K) || vmg_air(gc, diag, wall, 1, I, J, K - 1) || vmg_air(gc, diag, wall, 2, I, J, K) ||
+        vmg_air(gc, diag, wall, 2, I, J - 1, K))
+        coef[T + id] = 0.0f;
+    // edge along y at node (I,K): U(I,J,K), U(I,J,K-1), W(I,J,K), W(I-1,J,K)
+    if (vmg_air(gc, diag, wall, 0, I, J, K) || vmg_air(gc, diag, wall, 0, I, J, K - 1) || vmg_air(gc, diag, wall, 2, I, J, K) ||
+        vmg_air(gc, diag, wall, 2, I - 1, J, K))
+        coef[2 * T + id] = 0.0f;
+    // edge along z at node (I,J): U(I,J,K), U(I,J-1,K), V(I,J,K), V(I-1,J,K)
+    if (vmg_air(gc, diag, wall, 0, I, J, K) || vmg_air(gc, diag, wall, 0, I, J - 1, K) || vmg_air(gc, diag, wall, 1, I, J, K) ||
+        vmg_air(gc, diag, wall, 1, I - 1, J, K))
+        coef[3 * T + id] = 0.0f;
+}
+
+// coarse row diagonals (the 0/1 unknown flag arrives in diag and is overwritten)
 __global__ void __launch_bounds__(256) k_vmg_coarsen_rows(Grid gc, const float *__restrict__ coef, const float *__restrict__ vol,
-                                                          float *__restrict__ diag, float minvol) {
+                                                          float *__restrict__ diag) {
     int I, J, K;
     if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, gc.ni + 1, gc.nj + 1, gc.nk + 1, I, J, K)) return;
     size_t T = (size_t)gc.total;
     int id = gidx(gc, I, J, K), sy = SY(gc), sz = SZ(gc);
     const float *cc = coef, *cu = coef + T, *cv = coef + 2 * T, *cw = coef + 3 * T;
-    bool interior = I >= 1 && I < gc.ni && J >= 1 && J < gc.nj && K >= 1 && K < gc.nk;
     float dU = 0, dV = 0, dW = 0;
-    if (interior) {
-        // coarse unknowns need real mass: faces whose control volume holds (almost) no liquid form a
-        // singular block of the operator; they are left to the fine-level smoother
-        if (diag[id] != 0.0f && vol[id] >= minvol) dU = vol[id] + cc[id] + cc[id - 1] + cw[id + sy] + cw[id] + cv[id + sz] + cv[id];
-        if (diag[T + id] != 0.0f && vol[T + id] >= minvol) dV = vol[T + id] + cw[id + 1] + cw[id] + cc[id] + cc[id - sy] + cu[id + sz] + cu[id];
-        if (diag[2 * T + id] != 0.0f && vol[2 * T + id] >= minvol) dW = vol[2 * T + id] + cv[id + 1] + cv[id] + cu[id + sy] + cu[id] + cc[id] + cc[id - sz];
-    }
+    if (diag[id] != 0.0f) dU = vol[id] + cc[id] + cc[id - 1] + cw[id + sy] + cw[id] + cv[id + sz] + cv[id];
+    if (diag[T + id] != 0.0f) dV = vol[T + id] + cw[id + 1] + cw[id] + cc[id] + cc[id - sy] + cu[id + sz] + cu[id];
+    if (diag[2 * T + id] != 0.0f) dW = vol[2 * T + id] + cv[id + 1] + cv[id] + cu[id + sy] + cu[id] + cc[id] + cc[id - sz];
     diag[id] = dU; diag[T + id] = dV; diag[2 * T + id] = dW;
 }
