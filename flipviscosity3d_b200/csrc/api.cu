@@ -530,6 +530,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "use_graphs") s.use_graphs = (int)value;
     else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
+    else if (n == "viscosity_warm_start") s.visc_warm_start = (int)value;
     else if (n == "mg_sweeps") s.mg_sweeps = (int)value;
     else if (n == "mg_coarse_sweeps") s.mg_coarse_sweeps = (int)value;
     else if (n == "mg_omega") s.mg_omega = (float)value;

@@ -76,8 +76,8 @@ struct DiagViscosity {
 };
 
 // r holds b on entry.  x = 0, s = M^-1 r, partials of r.s and max|r|.
-template <int NC, class Diag>
-__global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag) {
+template <int NC, class Diag, bool KEEPX>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag, double *__restrict__ bmax_part) {
     __shared__ double sm[CG_THREADS / 32];
     const Grid &g = P.g;
     int nb = *P.blk_count;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag) {
             double r = d != 0.0f ? P.r[o] : 0.0;
             double z = d != 0.0f ? r / (double)d : 0.0;
             P.r[o] = r;
-            P.x[o] = 0.0;
+            if (!KEEPX) P.x[o] = 0.0;
             P.s[o] = z;
             rz += r * z;
             bm = fmax(bm, fabs(r));
@@ -102,18 +102,73 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag) {
     bm = cta_reduce<true>(bm, sm);
     if (threadIdx.x == 0) {
         P.part[gridDim.x + blockIdx.x] = rz;
-        P.part[2 * gridDim.x + blockIdx.x] = bm;
+        // with a warm start max|b| (the tolerance reference) was measured before r became b - A x0
+        if (!KEEPX) P.part[2 * gridDim.x + blockIdx.x] = bm;
+        else P.part[3 * gridDim.x + blockIdx.x] = bm;   // max|r0|, informational
+    }
+}
+
+// max|b| partials only (warm start: the relative tolerance refers to b, not to r0)
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
+    __shared__ double sm[CG_THREADS / 32];
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    double bm = 0.0;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++)
+            if (diag(m, id) != 0.0f) bm = fmax(bm, fabs(P.r[(size_t)m * g.total + id]));
+    }
+    bm = cta_reduce<true>(bm, sm);
+    if (threadIdx.x == 0) P.part[2 * gridDim.x + blockIdx.x] = bm;
+}
+
+// Warm start (x0 != 0): k_cg_guess puts the guess into s (so the phase-A kernel computes q = A x0),
+// k_cg_guess_residual then sets x = x0 and r = b - q; k_cg_init<KEEPX> continues from there.
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_guess(CGParams P, Diag diag, const float *__restrict__ guess) {
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            P.s[o] = diag(m, id) != 0.0f ? (double)guess[o] : 0.0;
+        }
+    }
+}
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg_guess_residual(CGParams P, Diag diag) {
+    const Grid &g = P.g;
+    int nb = *P.blk_count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            bool unk = diag(m, id) != 0.0f;
+            P.x[o] = unk ? P.s[o] : 0.0;
+            P.r[o] = unk ? P.r[o] - P.q[o] : 0.0;
+        }
     }
 }
 
 // single CTA: first CGState.  tol_rel > 0: tol = tol_rel * max|b| (pcgsolver.h:254-259), else tol_abs.
-static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int nparts, double tol_abs, double tol_rel, int maxit) {
+static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int nparts, double tol_abs, double tol_rel, int maxit,
+                                                                 int warm) {
     __shared__ double sm[CG_THREADS / 32];
     double rho = reduce_partials<false>(P.part + nparts, nparts, sm);
     double bmax = reduce_partials<true>(P.part + 2 * nparts, nparts, sm);
+    double r0max = warm ? reduce_partials<true>(P.part + 3 * nparts, nparts, sm) : bmax;
     if (threadIdx.x == 0) {
         CGState st;
-        st.rho = rho; st.resid = bmax; st.bmax = bmax;
+        st.rho = rho; st.resid = r0max; st.bmax = bmax;
         st.tol = tol_rel > 0 ? tol_rel * bmax : tol_abs;
         st.iter = 0; st.maxit = maxit; st.fail = 0; st.pad = 0;
         st.done = 0; st.converged = 0;
@@ -124,6 +179,8 @@ static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int 
             // pressure: max|b| < tol -> zero pressure (src/pressuresolver.cpp:173-175)
             if (bmax < tol_abs) { st.done = 1; st.converged = 1; }
         }
+        // a warm start may already satisfy the stopping rule
+        if (!st.done && warm && (P.strict ? r0max < st.tol : r0max <= st.tol)) { st.done = 1; st.converged = 1; }
         if (!st.done && (rho == 0 || rho != rho)) { st.done = 1; st.fail = 1; }
         P.st[0] = st;
         P.st[1] = st;
@@ -383,16 +440,34 @@ static void build_block_list(Sim &s, Diag diag) {
 // replayed; convergence is decided on the device, the host only polls the 64-byte state per chunk.
 template <int NC, class Diag, class ApplyFn>
 static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply,
-                      int graph_slot = -1) {
+                      int graph_slot = -1, const float *guess = nullptr) {
     int G = cg_grid(s);
-    auto kinit = &k_cg_init<NC, Diag>;
+    auto kinit = &k_cg_init<NC, Diag, false>;
+    auto kinit_keep = &k_cg_init<NC, Diag, true>;
     auto kupdate = &k_cg_update<NC, Diag, false>;
     auto kdir = &k_cg_direction<NC, Diag, false>;
-    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    if (guess) {
+        // r0 = b - A x0 with x0 = the guess; the tolerance stays relative to max|b|
+        auto kguess = &k_cg_guess<NC, Diag>;
+        auto kres = &k_cg_guess_residual<NC, Diag>;
+        auto kbmax = &k_cg_bmax<NC, Diag>;
+        FLIP_LAUNCH_SYNC(kbmax, G, CG_THREADS, s.stream, P, diag);
+        FLIP_LAUNCH(kguess, G, CG_THREADS, s.stream, P, diag, guess);
+        // the phase-A kernel tests st[parity].done: make sure slot 0 says "not done"
+        CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
+        apply(0);
+        FLIP_LAUNCH(kres, G, CG_THREADS, s.stream, P, diag);
+        FLIP_LAUNCH_SYNC(kinit_keep, G, CG_THREADS, s.stream, P, diag, (double *)nullptr);
+        s.kernel_launches += 5;
+    } else {
+        FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag, (double *)nullptr);
+        s.kernel_launches += 1;
+    }
     dist_reduce_partials(s, P.part + G, G, false);
     dist_reduce_partials(s, P.part + 2 * G, G, true);
-    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
-    s.kernel_launches += 2;
+    dist_reduce_partials(s, P.part + 3 * G, G, true);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, guess ? 1 : 0);
+    s.kernel_launches += 1;
     KERNEL_CHECK();
     int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
     auto launch_chunk = [&]() {
@@ -457,7 +532,7 @@ static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double t
     precond((const CGState *)nullptr);
     FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, -1);
     FLIP_LAUNCH(kstart, G, CG_THREADS, s.stream, P);
-    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, 0);
     s.kernel_launches += 4;
     KERNEL_CHECK();
     int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);

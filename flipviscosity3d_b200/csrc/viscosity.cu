@@ -489,7 +489,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
         h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
             dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
             FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity);
-        }, 1);
+        }, 1, s.visc_warm_start ? (const float *)s.vel : nullptr);
     }
     dist_allgather_slabs(s, s.cg_x, 3);
     // acceptance rule of src/viscositysolver.cpp:676-689
