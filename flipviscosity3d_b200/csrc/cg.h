@@ -58,6 +58,8 @@ struct CGParams {
     Grid g;
     const int *blk_list;
     const int *blk_count;
+    const int *cell_list;      // padded indices of the cells of the active blocks that hold >= 1 unknown
+    const int *cell_count;
     double *x, *r, *s, *q;     // [NC*total]
     double *z;                 // preconditioned residual (multigrid mode), or null for the diagonal
     double *part;              // [3*gridDim]: s.q | r.z | max|r|
@@ -80,12 +82,10 @@ template <int NC, class Diag, bool KEEPX>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag, double *__restrict__ bmax_part) {
     __shared__ double sm[CG_THREADS / 32];
     const Grid &g = P.g;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double rz = 0.0, bm = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             size_t o = (size_t)m * g.total + id;
             float d = diag(m, id);
@@ -113,12 +113,10 @@ template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
     const Grid &g = P.g;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double bm = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++)
             if (diag(m, id) != 0.0f) bm = fmax(bm, fabs(P.r[(size_t)m * g.total + id]));
     }
@@ -131,11 +129,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
 template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_guess(CGParams P, Diag diag, const float *__restrict__ guess) {
     const Grid &g = P.g;
-    int nb = *P.blk_count;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    int nc = *P.cell_count;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             size_t o = (size_t)m * g.total + id;
             P.s[o] = diag(m, id) != 0.0f ? (double)guess[o] : 0.0;
@@ -145,11 +141,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_guess(CGParams P, Diag diag, 
 template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_guess_residual(CGParams P, Diag diag) {
     const Grid &g = P.g;
-    int nb = *P.blk_count;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    int nc = *P.cell_count;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             size_t o = (size_t)m * g.total + id;
             bool unk = diag(m, id) != 0.0f;
@@ -196,19 +190,26 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag,
     const Grid &g = P.g;
     double sq = reduce_partials<false>(P.part, gridDim.x, sm);
     double alpha = st.rho / sq;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double rz = 0.0, rm = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
+        // all loads first (independent of the diagonal test): one memory round trip per cell
+        float dd[NC];
+        double sv[NC], qv[NC], xv[NC], rv[NC];
+#pragma unroll
         for (int m = 0; m < NC; m++) {
-            float d = diag(m, id);
+            size_t o = (size_t)m * g.total + id;
+            dd[m] = diag(m, id);
+            sv[m] = P.s[o]; qv[m] = P.q[o]; xv[m] = P.x[o]; rv[m] = P.r[o];
+        }
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            float d = dd[m];
             if (d == 0.0f) continue;
             size_t o = (size_t)m * g.total + id;
-            double s = P.s[o], q = P.q[o];
-            P.x[o] += alpha * s;
-            double r = P.r[o] - alpha * q;
+            P.x[o] = xv[m] + alpha * sv[m];
+            double r = rv[m] - alpha * qv[m];
             P.r[o] = r;
             if (!MG) rz += r * (r / (double)d);
             rm = fmax(rm, fabs(r));
@@ -228,12 +229,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
     __shared__ double sm[CG_THREADS / 32];
     if (parity >= 0 && P.st[parity].done) return;
     const Grid &g = P.g;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double rz = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             if (diag(m, id) == 0.0f) continue;
             size_t o = (size_t)m * g.total + id;
@@ -249,12 +248,10 @@ template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
     const Grid &g = P.g;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double bm = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             size_t o = (size_t)m * g.total + id;
             double r = diag(m, id) != 0.0f ? P.r[o] : 0.0;
@@ -270,11 +267,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag
 template <int NC>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_start_mg(CGParams P) {
     const Grid &g = P.g;
-    int nb = *P.blk_count;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    int nc = *P.cell_count;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             size_t o = (size_t)m * g.total + id;
             P.s[o] = P.z[o];
@@ -308,16 +303,24 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
     }
     if (conv || bad) return;
     double beta = rho_new / st.rho;
-    int nb = *P.blk_count;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    int nc = *P.cell_count;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
+        float dd[NC];
+        double zv[NC], sv[NC];
+#pragma unroll
         for (int m = 0; m < NC; m++) {
-            float d = diag(m, id);
+            size_t o = (size_t)m * g.total + id;
+            dd[m] = diag(m, id);
+            zv[m] = MG ? P.z[o] : P.r[o];
+            sv[m] = P.s[o];
+        }
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            float d = dd[m];
             if (d == 0.0f) continue;
             size_t o = (size_t)m * g.total + id;
-            P.s[o] = (MG ? P.z[o] : P.r[o] / (double)d) + beta * P.s[o];
+            P.s[o] = (MG ? zv[m] : zv[m] / (double)d) + beta * sv[m];
         }
     }
 }
@@ -405,6 +408,96 @@ __global__ void __launch_bounds__(CG_THREADS) k_count_unknowns(Grid g, const int
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
 }
 
+// ---- compact cell list -------------------------------------------------------------------
+// On the bench scene only ~23 % of the cells of an active block hold an unknown (ncu: warps half
+// empty, kernels latency bound).  The CG kernels therefore iterate over a compact, block-ordered
+// list of the cells that hold at least one unknown: every thread has work, loads stay localised
+// because the order is (block, then cell inside the block).
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cell_counts(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                             Diag diag, int *__restrict__ per_block) {
+    __shared__ int wsum[CG_THREADS / 32];
+    int nb = *count;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        bool has = false;
+        if (c.inside) {
+            int id = gidx(g, c.i, c.j, c.k);
+            for (int m = 0; m < NC; m++) has = has || diag(m, id) != 0.0f;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, has);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < CG_THREADS / 32; w++) t += wsum[w];
+            per_block[b] = t;
+        }
+    }
+}
+
+// single CTA: exclusive scan of per_block[0..*count) in place, total to *total
+static __global__ void __launch_bounds__(1024) k_scan_small(int *__restrict__ v, const int *__restrict__ count, int *__restrict__ total) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    int n = *count;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int id = base + threadIdx.x;
+        int x = id < n ? v[id] : 0;
+        int inc = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        int excl = carry_s + inc - x + (wid > 0 ? warp_sums[wid - 1] : 0);
+        if (id < n) v[id] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cell_fill(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                           Diag diag, const int *__restrict__ offset, int *__restrict__ cells) {
+    __shared__ int wsum[CG_THREADS / 32];
+    int nb = *count;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        bool has = false;
+        int id = 0;
+        if (c.inside) {
+            id = gidx(g, c.i, c.j, c.k);
+            for (int m = 0; m < NC; m++) has = has || diag(m, id) != 0.0f;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, has);
+        __syncthreads();
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < wid; w++) before += wsum[w];
+        int rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (has) cells[offset[b] + rank] = id;
+    }
+}
+
 static inline int cg_grid(const Sim &s) {
     int gsz = s.num_sms * s.cg_grid_mult;
     return gsz > FLIP_CG_MAXGRID ? FLIP_CG_MAXGRID : gsz;
@@ -426,6 +519,14 @@ static void build_block_list(Sim &s, Diag diag) {
     FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag);
     FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count,
                      s.bz0 * g.nbx * g.nby, s.bz1 * g.nbx * g.nby);
+    // compact cell list of this solve
+    auto kcc = &k_cell_counts<NC, Diag>;
+    auto kcf = &k_cell_fill<NC, Diag>;
+    FLIP_LAUNCH_SYNC(kcc, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.blk_flag);
+    FLIP_LAUNCH_SYNC(k_scan_small, 1, 1024, s.stream, s.blk_flag, (const int *)s.blk_count, s.cell_count);
+    FLIP_LAUNCH_SYNC(kcf, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag,
+                     (const int *)s.blk_flag, s.cell_list);
+    s.kernel_launches += 3;
     auto kcount = &k_count_unknowns<NC, Diag>;
     CUDA_CHECK(cudaMemsetAsync(s.unk_count, 0, sizeof(int), s.stream));
     FLIP_LAUNCH_SYNC(kcount, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.unk_count);
@@ -482,7 +583,8 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
         }
     };
 #ifndef FLIP_CPU_EMU
-    bool use_graph = s.use_graphs && s.nranks == 1 && graph_slot >= 0 && graph_slot < 2;
+    // NCCL calls are stream-captured with the kernels (multi-GPU: use_graphs >= 2 opts in)
+    bool use_graph = s.use_graphs && (s.nranks == 1 || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
     if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk)) {
         if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
         cudaGraph_t graph = nullptr;

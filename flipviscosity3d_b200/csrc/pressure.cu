@@ -74,12 +74,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const
     const Grid &g = P.g;
     const int sy = SY(g), sz = SZ(g);
     const double *__restrict__ s = P.s;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double sq = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         float4 a = coef[id];
         if (a.x == 0.0f) continue;
         double sc = s[id];
@@ -121,7 +119,7 @@ void solve_pressure(Sim &s, float dt) {
     // the search direction is read with a one-cell halo: it must be zero outside the active blocks
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * (size_t)g.total, s.stream));
     CGParams P;
-    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count;
+    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
     P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
     P.part = s.part; P.st = s.cgst; P.strict = 1;
     int G = cg_grid(s);

@@ -43,7 +43,7 @@ struct Sim {
     double visc_accept = 10.0;          // src/viscositysolver.h:201
     int visc_maxit = 700;               // src/viscositysolver.h:202
     int visc_maxit_scale = 40;
-    int visc_warm_start = 1;            // start the viscosity CG from the current velocity instead of 0
+    int visc_warm_start = 0;            // start the viscosity CG from the current velocity instead of 0
     int visc_precond = 0;               // 0 = diagonal (default), 1 = multigrid V-cycle (vmg.h, experimental)
     int mg_sweeps = 2;                  // damped-Jacobi sweeps before = after the coarse correction
     int mg_coarse_sweeps = 24;
@@ -53,7 +53,7 @@ struct Sim {
     float mg_alpha = 1.0f;              // scale of the coarse-grid correction
     int mg_levels = 8;                  // cap on the number of levels
     int cg_chunk = 32;
-    int cg_grid_mult = 3;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
+    int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
     int verbose = 0;
     int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph (1 GPU)
     void *cg_graph[2] = {0, 0};         // cudaGraphExec_t: [0] pressure, [1] viscosity
@@ -99,6 +99,8 @@ struct Sim {
     int *blk_flag = 0;        // [nblocks]
     int *blk_list = 0;        // [nblocks]
     int *blk_count = 0;       // [1]
+    int *cell_list = 0;       // [total] compact list of cells with >= 1 unknown (this solve)
+    int *cell_count = 0;      // [1]
     double *part = 0;         // [4*FLIP_CG_MAXGRID] reduction partials
     CGState *cgst = 0;        // [2] ping-pong
     CGState *cgst_host = 0;   // pinned

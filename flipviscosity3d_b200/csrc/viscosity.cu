@@ -247,12 +247,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
     const float *__restrict__ cc = vcoef, *__restrict__ cu = vcoef + T, *__restrict__ cv = vcoef + 2 * T,
                 *__restrict__ cw = vcoef + 3 * T;
     const double *__restrict__ su = P.s, *__restrict__ sv = P.s + T, *__restrict__ sw = P.s + 2 * T;
-    int nb = *P.blk_count;
+    int nc = *P.cell_count;
     double sq = 0.0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, P.blk_list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
         float dU = vdiag[id], dV = vdiag[T + id], dW = vdiag[2 * T + id];
         if (dU == 0.0f && dV == 0.0f && dW == 0.0f) continue;
         double u0 = su[id], v0 = sv[id], w0 = sw[id];
@@ -470,7 +468,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     build_block_list<3>(s, diag);
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
     CGParams P;
-    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count;
+    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
     P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
     P.part = s.part; P.st = s.cgst; P.strict = 0;
     int G = cg_grid(s);
