@@ -104,10 +104,11 @@ void sim_reserve_particles(Sim &s, long long n) {
 
 void sim_free(Sim &s) {
     cudaStreamSynchronize(s.stream);
-    try { dist_shutdown(s); } catch (...) {}
 #ifndef FLIP_CPU_EMU
+    // graphs may hold captured NCCL kernels: destroy them before the communicator
     for (int q = 0; q < 2; q++) if (s.cg_graph[q]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[q]); s.cg_graph[q] = 0; }
 #endif
+    try { dist_shutdown(s); } catch (...) {}
     viscosity_free(s);
     free_particles(s);
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
