@@ -5,7 +5,7 @@ import bench
 from flipviscosity3d_b200 import FlipSim
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 phi, p = bench.build_scene(n)
-for kw in [dict(), dict(cg_grid_mult=2), dict(cg_grid_mult=4), dict(cg_grid_mult=6)]:
+for kw in [dict(cg_grid_mult=1), dict(cg_grid_mult=2), dict(cg_grid_mult=3)]:
     sim = FlipSim(n, n, n, 1.0 / n)
     sim.set_solid_sdf(phi); sim.set_particles(p); sim.set_viscosity(5.0)
     for k, v in kw.items(): sim.set_param(k, v)
