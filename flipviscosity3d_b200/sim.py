@@ -58,10 +58,13 @@ class FlipSim:
         ni, nj, nk = self.ni, self.nj, self.nk
         cells, nodes = (nk, nj, ni), (nk + 1, nj + 1, ni + 1)
         u, v, w = (nk, nj, ni + 1), (nk, nj + 1, ni), (nk + 1, nj, ni)
-        return {F_LIQUID_SDF: cells, F_SOLID_SDF: nodes, F_U: u, F_V: v, F_W: w, F_SAVED_U: u, F_SAVED_V: v,
+        shapes = {F_LIQUID_SDF: cells, F_SOLID_SDF: nodes, F_U: u, F_V: v, F_W: w, F_SAVED_U: u, F_SAVED_V: v,
                 F_SAVED_W: w, F_WEIGHT_U: u, F_WEIGHT_V: v, F_WEIGHT_W: w, F_PRESSURE: cells, F_VISCOSITY: nodes,
                 F_VOL_CENTER: cells, F_VOL_U: u, F_VOL_V: v, F_VOL_W: w, F_VOL_EDGE_U: (nk + 1, nj + 1, ni),
-                F_VOL_EDGE_V: (nk + 1, nj, ni + 1), F_VOL_EDGE_W: (nk, nj + 1, ni + 1)}[f]
+                F_VOL_EDGE_V: (nk + 1, nj, ni + 1), F_VOL_EDGE_W: (nk, nj + 1, ni + 1)}
+        if f not in shapes:
+            raise FlipError("unknown field id %r (see include/flip_b200.h)" % (f,))
+        return shapes[f]
 
     # ---- scene ----
     def set_solid_sdf(self, phi):
