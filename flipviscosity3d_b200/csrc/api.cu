@@ -56,6 +56,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s.cg_s, 3 * T);
     dev_alloc(s.cg_q, 3 * T);
     dev_alloc(s.cg_z, 3 * T);
+    dev_alloc(s.cg_w, 3 * T);
     dev_alloc(s.vvol, 7 * T);
     dev_alloc(s.vnode, 7 * T);
     dev_alloc(s.vvalid, T);
@@ -67,7 +68,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s.unk_count, 1);
     dev_alloc(s.cell_list, T);
     dev_alloc(s.cell_count, 1);
-    dev_alloc(s.part, 4 * (size_t)FLIP_CG_MAXGRID);
+    dev_alloc(s.part, 6 * (size_t)FLIP_CG_MAXGRID);
     dev_alloc(s.cgst, 2);
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
     CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
@@ -113,7 +114,7 @@ void sim_free(Sim &s) {
     free_particles(s);
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
                     s.weight, s.valid, s.layer, s.fstate, s.viscosity, s.pressure, s.maxvel_dev, s.pcoef, s.cg_x,
-                    s.cg_r, s.cg_s, s.cg_q, s.cg_z, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
+                    s.cg_r, s.cg_s, s.cg_q, s.cg_z, s.cg_w, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
                     s.blk_count, s.unk_count, s.cell_list, s.cell_count, s.part, s.cgst};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
@@ -531,6 +532,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "maxit_scale") { s.pressure_maxit_scale = (int)value; s.visc_maxit_scale = (int)value; }
     else if (n == "cg_chunk") s.cg_chunk = (int)value;
     else if (n == "use_graphs") s.use_graphs = (int)value;
+    else if (n == "cg_variant") { s.cg_variant = (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
     else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
     else if (n == "viscosity_warm_start") s.visc_warm_start = (int)value;

@@ -164,7 +164,7 @@ static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int 
         CGState st;
         st.rho = rho; st.resid = r0max; st.bmax = bmax;
         st.tol = tol_rel > 0 ? tol_rel * bmax : tol_abs;
-        st.iter = 0; st.maxit = maxit; st.fail = 0; st.pad = 0;
+        st.iter = 0; st.maxit = maxit; st.fail = 0; st.first = 1; st.alpha = 0.0;
         st.done = 0; st.converged = 0;
         if (tol_rel > 0) {
             // viscosity: zero rhs -> solution 0, success (pcgsolver.h:254-258)
@@ -654,6 +654,193 @@ static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double t
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
             s.kernel_launches += 4;
         }
+        KERNEL_CHECK();
+        launched += chunk;
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-reduction CG (Chronopoulos & Gear recurrences), diagonal preconditioner.
+//
+//   u = M^-1 r,  w = A u,  gamma = r.u,  delta = w.u
+//   beta = gamma/gamma_old,  alpha = gamma / (delta - beta*gamma/alpha_old)
+//   p = u + beta p,  s = w + beta s (= A p),  x += alpha p,  r -= alpha s
+//
+// Two kernels per iteration instead of three and ONE point where scalars are needed:
+//   K1 (k_cg2_step)  reduces the partials of gamma, delta and max|r| left by the previous iteration,
+//                    decides convergence, updates p, s, x, r, u in one pass and leaves the partials
+//                    of the new gamma and max|r| (ping-pong buffers: other CTAs still read the old);
+//   K2 (phase-A stencil kernel, unchanged, with s:=u and q:=w) computes w = A u and the partials of
+//                    delta.
+// On several GPUs that is one 2-element sum all-reduce + one max all-reduce per iteration instead of
+// three scalar all-reduces.  Same operator, same stopping rule (max|r| against the tolerance, tested
+// on the residual BEFORE each update), same converged solution as run_cg.
+// Partials: [0,G) delta | [G,2G) gamma(0) | [2G,3G) rmax(0) | [3G,4G) gamma(1) | [4G,5G) rmax(1)
+// ------------------------------------------------------------------------------------------
+struct CG2Params {
+    CGParams P;      // x, r, s(=p), q(=s=Ap) as in CGParams; z = u
+    double *w;       // w = A u
+};
+
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg2_init(CG2Params Q, Diag diag) {
+    __shared__ double sm[CG_THREADS / 32];
+    const CGParams &P = Q.P;
+    const Grid &g = P.g;
+    int nc = *P.cell_count;
+    double gam = 0.0, bm = 0.0;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
+        int id = P.cell_list[qq];
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            float d = diag(m, id);
+            double r = d != 0.0f ? P.r[o] : 0.0;
+            double u = d != 0.0f ? r / (double)d : 0.0;
+            P.r[o] = r;
+            P.x[o] = 0.0;
+            P.z[o] = u;
+            gam += r * u;
+            bm = fmax(bm, fabs(r));
+        }
+    }
+    gam = cta_reduce<false>(gam, sm);
+    bm = cta_reduce<true>(bm, sm);
+    if (threadIdx.x == 0) {
+        P.part[gridDim.x + blockIdx.x] = gam;        // gamma(0)
+        P.part[2 * gridDim.x + blockIdx.x] = bm;     // rmax(0) = max|b|
+    }
+}
+
+template <int NC, class Diag>
+__global__ void __launch_bounds__(CG_THREADS) k_cg2_step(CG2Params Q, Diag diag, int parity) {
+    __shared__ double sm[CG_THREADS / 32];
+    const CGParams &P = Q.P;
+    const CGState st = P.st[parity];
+    const int G = gridDim.x;
+    if (st.done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) P.st[parity ^ 1] = st;
+        return;
+    }
+    const double *gpart = P.part + (parity ? 3 : 1) * G, *mpart = P.part + (parity ? 4 : 2) * G;
+    double *gnext = P.part + (parity ? 1 : 3) * G, *mnext = P.part + (parity ? 2 : 4) * G;
+    double rmax = reduce_partials<true>(mpart, G, sm);
+    double gam = reduce_partials<false>(gpart, G, sm);
+    double del = reduce_partials<false>(P.part, G, sm);
+    bool conv = P.strict ? (rmax < st.tol) : (rmax <= st.tol);
+    double beta = st.first ? 0.0 : gam / st.rho;
+    double alpha = st.first ? gam / del : gam / (del - beta * gam / st.alpha);
+    bool bad = !(alpha == alpha) || !(rmax == rmax) || (st.first && (gam == 0 || !(gam == gam)));
+    bool stop = conv || bad || st.iter >= st.maxit;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CGState nx = st;
+        nx.resid = rmax;
+        nx.converged = conv ? 1 : 0;
+        nx.done = stop ? 1 : 0;
+        if (bad && !conv) nx.fail = 1;
+        if (!stop) { nx.iter = st.iter + 1; nx.rho = gam; nx.alpha = alpha; nx.first = 0; }
+        P.st[parity ^ 1] = nx;
+    }
+    if (stop) return;
+    const Grid &g = P.g;
+    const bool first = st.first != 0;
+    int nc = *P.cell_count;
+    double gnew = 0.0, rm = 0.0;
+    for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += G * CG_THREADS) {
+        int id = P.cell_list[qq];
+        float dd[NC];
+        double uv[NC], wv[NC], pv[NC], sv[NC], xv[NC], rv[NC];
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            size_t o = (size_t)m * g.total + id;
+            dd[m] = diag(m, id);
+            uv[m] = P.z[o]; wv[m] = Q.w[o]; xv[m] = P.x[o]; rv[m] = P.r[o];
+            pv[m] = first ? 0.0 : P.s[o];
+            sv[m] = first ? 0.0 : P.q[o];
+        }
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            float d = dd[m];
+            if (d == 0.0f) continue;
+            size_t o = (size_t)m * g.total + id;
+            double pn = uv[m] + beta * pv[m];
+            double sn = wv[m] + beta * sv[m];
+            double r = rv[m] - alpha * sn;
+            double u = r / (double)d;
+            P.s[o] = pn;
+            P.q[o] = sn;
+            P.x[o] = xv[m] + alpha * pn;
+            P.r[o] = r;
+            P.z[o] = u;
+            gnew += r * u;
+            rm = fmax(rm, fabs(r));
+        }
+    }
+    gnew = cta_reduce<false>(gnew, sm);
+    rm = cta_reduce<true>(rm, sm);
+    if (threadIdx.x == 0) { gnext[blockIdx.x] = gnew; mnext[blockIdx.x] = rm; }
+}
+
+// `apply_uw(parity)` must launch the phase-A kernel on a CGParams whose s is u (P.z) and q is w:
+// it computes w = A u and leaves the partials of u.w in part[0,G).
+template <int NC, class Diag, class ApplyFn>
+static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply_uw, int graph_slot) {
+    int G = cg_grid(s);
+    CG2Params Q;
+    Q.P = P; Q.P.z = s.cg_z; Q.w = s.cg_w;
+    auto kinit = &k_cg2_init<NC, Diag>;
+    auto kstep = &k_cg2_step<NC, Diag>;
+    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, Q, diag);
+    dist_reduce_partials(s, P.part + G, G, false);
+    dist_reduce_partials(s, P.part + 2 * G, G, true);
+    // first CGState: reuses k_cg_begin (rho := gamma0, tolerance, trivial-rhs exits)
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, 0);
+    apply_uw(0);
+    dist_reduce_partials(s, P.part, G, false);
+    s.kernel_launches += 3;
+    KERNEL_CHECK();
+    int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
+    auto launch_chunk = [&]() {
+        for (int it = 0; it < chunk; it++) {
+            int parity = it & 1;
+            FLIP_LAUNCH_SYNC(kstep, G, CG_THREADS, s.stream, Q, diag, parity);
+            dist_reduce_partials(s, P.part + (parity ? 1 : 3) * G, G, false);
+            dist_reduce_partials(s, P.part + (parity ? 2 : 4) * G, G, true);
+            apply_uw(parity ^ 1);
+            dist_reduce_partials(s, P.part, G, false);
+        }
+    };
+#ifndef FLIP_CPU_EMU
+    bool use_graph = s.use_graphs && (s.nranks == 1 || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
+    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk + 1000)) {
+        if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        launch_chunk();
+        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        s.cg_graph[graph_slot] = (void *)exec;
+        s.cg_graph_chunk[graph_slot] = chunk + 1000;   // tag: graph of the single-reduction variant
+    }
+#else
+    bool use_graph = false;
+#endif
+    CGState h;
+    int launched = 0;
+    while (true) {
+        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h = *s.cgst_host;
+        if (h.done || launched >= maxit + 2 * chunk) break;
+#ifndef FLIP_CPU_EMU
+        if (use_graph) CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream));
+        else
+#endif
+            launch_chunk();
+        s.kernel_launches += 2 * chunk;
         KERNEL_CHECK();
         launched += chunk;
     }

@@ -125,10 +125,23 @@ void solve_pressure(Sim &s, float dt) {
     int G = cg_grid(s);
     const float4 *coef = s.pcoef;
     cudaStream_t st = s.stream;
-    CGState h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, s.pressure_maxit * s.pressure_maxit_scale, [&](int parity) {
-        dist_halo_exchange(s, P.s, 1);   // one ghost plane of the search direction per stencil apply
-        FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, P, coef, parity);
-    }, 0);
+    int pmaxit = s.pressure_maxit * s.pressure_maxit_scale;
+    CGState h;
+    if (s.cg_variant == 1) {
+        // the search direction of the stencil kernel is u = M^-1 r here: it needs the zero halo too
+        CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * (size_t)g.total, s.stream));
+        CGParams Pu = P;
+        Pu.s = s.cg_z; Pu.q = s.cg_w;
+        h = run_cg2<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, [&](int parity) {
+            dist_halo_exchange(s, Pu.s, 1);
+            FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, Pu, coef, parity);
+        }, 0);
+    } else {
+        h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, [&](int parity) {
+            dist_halo_exchange(s, P.s, 1);   // one ghost plane of the search direction per stencil apply
+            FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, P, coef, parity);
+        }, 0);
+    }
     dist_allgather_slabs(s, s.cg_x, 1);
     long long nc = (long long)g.ni * g.nj * g.nk;
     FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);

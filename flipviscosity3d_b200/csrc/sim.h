@@ -14,7 +14,8 @@ struct CGState {
     int converged;   // 1 = resid under tol
     int maxit;
     int fail;        // 1 = rho was 0/NaN at start (pcgsolver.h:264-267)
-    int pad;
+    int first;       // single-reduction variant: no previous direction yet
+    double alpha;    // single-reduction variant: previous step length
 };
 
 struct SolveStats {
@@ -53,6 +54,8 @@ struct Sim {
     float mg_alpha = 1.0f;              // scale of the coarse-grid correction
     int mg_levels = 8;                  // cap on the number of levels
     int cg_chunk = 32;
+    int cg_variant = 1;                 // 0 = textbook PCG (3 kernels, 2 reduction points per iteration),
+                                        // 1 = single-reduction Chronopoulos-Gear recurrences (2 kernels)
     int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
     int verbose = 0;
     int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph (1 GPU)
@@ -89,7 +92,8 @@ struct Sim {
     // --- solver workspaces ---
     float4 *pcoef = 0;        // pressure stencil {diag, +i, +j, +k}
     double *cg_x = 0, *cg_r = 0, *cg_s = 0, *cg_q = 0;   // [3*total] (pressure uses component 0)
-    double *cg_z = 0;         // [3*total] preconditioned residual (multigrid mode)
+    double *cg_z = 0;         // [3*total] preconditioned residual (multigrid mode; u = M^-1 r in the single-reduction CG)
+    double *cg_w = 0;         // [3*total] w = A u (single-reduction CG)
     void *vmg = 0;            // viscosity multigrid hierarchy (VMG*, viscosity.cu)
     float *vvol = 0;          // 7 volume grids [7*total]: center,U,V,W,edgeU,edgeV,edgeW
     float *vnode = 0;         // 7 nodal phi grids [7*total]

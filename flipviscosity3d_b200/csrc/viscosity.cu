@@ -493,6 +493,14 @@ void stage_apply_viscosity(Sim &s, float dt) {
         h = run_cg_mg<3>(s, P, diag, 0.0, s.visc_tol, maxit,
                          [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity); },
                          [&](const CGState *cst) { vmg_vcycle(s, *M, (const double *)P.r, P.z, cst); });
+    } else if (s.cg_variant == 1) {
+        CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
+        CGParams Pu = P;
+        Pu.s = s.cg_z; Pu.q = s.cg_w;
+        h = run_cg2<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
+            dist_halo_exchange(s, Pu.s, 3);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Pu, vcoef, vdiag, parity);
+        }, 1);
     } else {
         h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
             dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
