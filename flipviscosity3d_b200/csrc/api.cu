@@ -532,7 +532,9 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "maxit_scale") { s.pressure_maxit_scale = (int)value; s.visc_maxit_scale = (int)value; }
     else if (n == "cg_chunk") s.cg_chunk = (int)value;
     else if (n == "use_graphs") s.use_graphs = (int)value;
-    else if (n == "cg_variant") { s.cg_variant = (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
+    else if (n == "cg_variant") { s.cg_variant_pressure = s.cg_variant_viscosity = (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
+    else if (n == "cg_variant_pressure") { s.cg_variant_pressure = (int)value; s.cg_graph_chunk[0] = -1; }
+    else if (n == "cg_variant_viscosity") { s.cg_variant_viscosity = (int)value; s.cg_graph_chunk[1] = -1; }
     else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
     else if (n == "viscosity_warm_start") s.visc_warm_start = (int)value;

@@ -127,7 +127,7 @@ void solve_pressure(Sim &s, float dt) {
     cudaStream_t st = s.stream;
     int pmaxit = s.pressure_maxit * s.pressure_maxit_scale;
     CGState h;
-    if (s.cg_variant == 1) {
+    if (s.cg_variant_pressure == 1) {
         // the search direction of the stencil kernel is u = M^-1 r here: it needs the zero halo too
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * (size_t)g.total, s.stream));
         CGParams Pu = P;

@@ -54,8 +54,12 @@ struct Sim {
     float mg_alpha = 1.0f;              // scale of the coarse-grid correction
     int mg_levels = 8;                  // cap on the number of levels
     int cg_chunk = 32;
-    int cg_variant = 1;                 // 0 = textbook PCG (3 kernels, 2 reduction points per iteration),
-                                        // 1 = single-reduction Chronopoulos-Gear recurrences (2 kernels)
+    // 0 = textbook PCG (3 kernels, 2 reduction points per iteration), 1 = single-reduction
+    // Chronopoulos-Gear recurrences (2 kernels).  Measured on B200 at 256^3: the fused update kernel wins
+    // for the scalar pressure system (9.3 vs 10.5 ms) and loses for the 3-component viscosity system
+    // (86 vs 70 us/iteration: 18 fp64 values in flight per thread cost occupancy).
+    int cg_variant_pressure = 1;
+    int cg_variant_viscosity = 0;
     int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
     int verbose = 0;
     int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph (1 GPU)

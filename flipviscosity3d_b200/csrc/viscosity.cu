@@ -493,7 +493,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
         h = run_cg_mg<3>(s, P, diag, 0.0, s.visc_tol, maxit,
                          [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity); },
                          [&](const CGState *cst) { vmg_vcycle(s, *M, (const double *)P.r, P.z, cst); });
-    } else if (s.cg_variant == 1) {
+    } else if (s.cg_variant_viscosity == 1) {
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
