@@ -150,7 +150,7 @@ def run_reference(args):
 def workload_config(args, particles):
     return {"workload": "bunny_in_sphere_%d^3_8ppc_viscosity%g (BASELINE.json configs[3])" % (args.size, args.viscosity),
             "grid": [args.size] * 3, "particles": int(particles), "viscosity": args.viscosity, "frame_dt": FRAME_DT,
-            "step": "one substep of FluidSimulation::advance", "parallelism": "k-slab CG x%d (particle/grid stages replicated)" % args.gpus,
+            "step": "one substep of FluidSimulation::advance", "parallelism": "k-slab CG x%d (particle/grid stages replicated; per-iteration exchanges %s)" % (args.gpus, "NCCL" if getattr(args, "no_p2p", False) else "peer memory over NVLink"),
             "l2": "working set (fields + CG vectors of the active blocks) exceeds the 126 MB L2; no flush between steps"}
 
 
@@ -183,6 +183,11 @@ def run_b200(args):
         box = [sim.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         sim.dist_init(rank, world, box[0])
+        if not args.no_p2p:
+            # per-iteration reductions / halos through peer memory (CUDA IPC) instead of NCCL
+            blobs = [None] * world
+            dist.all_gather_object(blobs, sim.dist_p2p_export())
+            sim.dist_p2p_import(blobs)
 
     def barrier_sync():
         if world > 1:
@@ -286,6 +291,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--viscosity", type=float, default=5.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: keep NCCL for the per-iteration exchanges")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -64,6 +64,9 @@ SYMBOLS = {
     "flip_get_stats": (C.c_int, [_H, C.POINTER(flip_stats)]),
     "flip_dist_unique_id": (C.c_int, [C.c_void_p]),
     "flip_dist_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "flip_dist_p2p_blob_size": (C.c_int, []),
+    "flip_dist_p2p_export": (C.c_int, [_H, C.c_void_p]),
+    "flip_dist_p2p_import": (C.c_int, [_H, C.c_void_p]),
     "flip_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "flip_host_free": (C.c_int, [C.c_void_p]),
     "flip_version": (C.c_char_p, []),

@@ -592,6 +592,22 @@ int flip_dist_init(flip_sim *h, int rank, int nranks, const void *unique_id128) 
     return FLIP_OK;
 }
 
+int flip_dist_p2p_blob_size(void) { return dist_p2p_blob_size(); }
+
+int flip_dist_p2p_export(flip_sim *h, void *out) {
+    API_BEGIN(h)
+    if (!out) return fail_inval(s, "flip_dist_p2p_export: null pointer");
+    dist_p2p_export(s, out);
+    API_END()
+}
+
+int flip_dist_p2p_import(flip_sim *h, const void *all_blobs) {
+    API_BEGIN(h)
+    if (!all_blobs) return fail_inval(s, "flip_dist_p2p_import: null pointer");
+    dist_p2p_import(s, all_blobs);
+    API_END()
+}
+
 int flip_host_alloc(void **ptr, uint64_t bytes) {
     if (!ptr) return FLIP_EINVAL;
     return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? FLIP_OK : FLIP_ENOMEM;

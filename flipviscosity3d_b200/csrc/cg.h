@@ -584,7 +584,7 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
     };
 #ifndef FLIP_CPU_EMU
     // NCCL calls are stream-captured with the kernels (multi-GPU: use_graphs >= 2 opts in)
-    bool use_graph = s.use_graphs && (s.nranks == 1 || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
+    bool use_graph = s.use_graphs && (s.nranks == 1 || dist_p2p_active(s) || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
     if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk)) {
         if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -812,7 +812,7 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
         }
     };
 #ifndef FLIP_CPU_EMU
-    bool use_graph = s.use_graphs && (s.nranks == 1 || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
+    bool use_graph = s.use_graphs && (s.nranks == 1 || dist_p2p_active(s) || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
     if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk + 1000)) {
         if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
         cudaGraph_t graph = nullptr;

@@ -118,6 +118,7 @@ void dist_init(Sim &s, int rank, int nranks, const void *unique_id) {
 }
 
 void dist_shutdown(Sim &s) {
+    dist_p2p_shutdown(s);
     if (s.nccl) { ncclCommDestroy((ncclComm_t)s.nccl); s.nccl = 0; }
     s.rank = 0; s.nranks = 1;
     dist_setup_slab(s);
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(512) k_collapse_partials(double *__restrict__ 
 
 void dist_reduce_partials(Sim &s, double *part, int n, bool is_max) {
     if (s.nranks == 1) return;
+    if (dist_p2p_active(s)) { dist_p2p_reduce(s, part, n, is_max); return; }
     k_collapse_partials<<<1, 512, 0, s.stream>>>(part, n, is_max ? 1 : 0);
     s.kernel_launches++;
     NCCL_CHECK(ncclAllReduce(part, part, 1, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)s.nccl, s.stream));
@@ -160,6 +162,7 @@ static inline size_t plane_offset(const Grid &g, int k) { return (size_t)(k + FL
 // slab is the ghost layer the 7-point and the coupled-face stencils read.
 void dist_halo_exchange(Sim &s, double *field, int ncomp) {
     if (s.nranks == 1) return;
+    if (dist_p2p_active(s)) { dist_p2p_halo(s, field, ncomp); return; }
     const Grid &g = s.g;
     ncclComm_t comm = (ncclComm_t)s.nccl;
     int k0 = FLIP_B * s.bz0, k1 = FLIP_B * s.bz1;   // k1 may exceed nk+1 on the last rank (no upper neighbour then)

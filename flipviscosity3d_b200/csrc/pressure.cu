@@ -147,6 +147,7 @@ void solve_pressure(Sim &s, float dt) {
     FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);
     s.kernel_launches++;
     KERNEL_CHECK();
+    if (dist_p2p_status(s) != 0) throw FlipError("multi-GPU peer-memory exchange timed out (a rank is missing or out of step)");
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));

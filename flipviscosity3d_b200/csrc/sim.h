@@ -118,6 +118,7 @@ struct Sim {
     // --- multi-GPU: 1-D slab decomposition of the solver blocks along k (dist.cu) ---
     int rank = 0, nranks = 1;
     void *nccl = 0;           // ncclComm_t
+    void *p2p = 0;            // P2PState* (p2p.cu): peer-memory mailboxes for the per-iteration exchanges
     int bz0 = 0, bz1 = 0;     // owned range of 8-cell block layers in k: [bz0, bz1)
 
     // stats of the last substep
@@ -165,6 +166,15 @@ void dist_reduce_partials(Sim &s, double *part, int n, bool is_max);   // collap
 void dist_halo_exchange(Sim &s, double *field, int ncomp);            // one ghost plane each side of the slab
 void dist_allgather_slabs(Sim &s, double *field, int ncomp);          // every rank gets every slab
 void dist_allreduce_int(Sim &s, int *dev_value);
+// p2p.cu
+int dist_p2p_blob_size();
+void dist_p2p_export(Sim &s, void *out);
+void dist_p2p_import(Sim &s, const void *all_blobs);
+void dist_p2p_shutdown(Sim &s);
+bool dist_p2p_active(Sim &s);
+int dist_p2p_status(Sim &s);
+void dist_p2p_reduce(Sim &s, double *part, int n, bool is_max);
+void dist_p2p_halo(Sim &s, double *field, int ncomp);
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);

@@ -515,6 +515,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
         s.kernel_launches++;
     }
     KERNEL_CHECK();
+    if (dist_p2p_status(s) != 0) throw FlipError("multi-GPU peer-memory exchange timed out (a rank is missing or out of step)");
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
@@ -566,6 +567,42 @@ extern "C" int flip_debug_vmg_apply(void *hsim, const double *r_host, double *z_
         vmg_vcycle(s, *M, (const double *)s.cg_q, s.cg_z, nullptr);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(z_host, s.cg_z, n * sizeof(double), cudaMemcpyDeviceToHost));
+    } catch (...) { return -2; }
+    return 0;
+}
+
+// y = A x for the viscosity system of the last solve, on raw padded fp64 arrays [3*total] (tests /
+// solver prototyping only).  Also: raw access to the row diagonals and face volumes.
+extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y_host) {
+    Sim &s = *(Sim *)hsim;
+    const Grid &g = s.g;
+    size_t n = 3 * (size_t)g.total;
+    try {
+        CUDA_CHECK(cudaMemcpy(s.cg_z, x_host, n * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemsetAsync(s.cg_w, 0, n * sizeof(double), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
+        CGParams P;
+        P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
+        P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_z; P.q = s.cg_w; P.z = nullptr;
+        P.part = s.part; P.st = s.cgst; P.strict = 0;
+        FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, 0);
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        CUDA_CHECK(cudaMemcpy(y_host, s.cg_w, n * sizeof(double), cudaMemcpyDeviceToHost));
+    } catch (...) { return -2; }
+    return 0;
+}
+extern "C" int flip_debug_visc_rhs(void *hsim, double *b_host, float *diag_host, float *vol_host /*3T: U,V,W*/) {
+    Sim &s = *(Sim *)hsim;
+    size_t T = (size_t)s.g.total;
+    // the rhs of the last solve is gone (r was consumed); recompute rows
+    try {
+        long long n1 = (long long)(s.g.ni + 1) * (s.g.nj + 1) * (s.g.nk + 1);
+        FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, s.g, (const float *)s.vvol, (const float *)s.vcoef,
+                    (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r);
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        CUDA_CHECK(cudaMemcpy(b_host, s.cg_r, 3 * T * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(diag_host, s.vdiag, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(vol_host, s.vvol + T, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
     } catch (...) { return -2; }
     return 0;
 }

@@ -204,6 +204,17 @@ class FlipSim:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._ck(self.lib.flip_dist_init(self.h, int(rank), int(nranks), buf))
 
+    def dist_p2p_export(self):
+        n = self.lib.flip_dist_p2p_blob_size()
+        buf = C.create_string_buffer(n)
+        self._ck(self.lib.flip_dist_p2p_export(self.h, buf))
+        return buf.raw
+
+    def dist_p2p_import(self, blobs_in_rank_order):
+        data = b"".join(blobs_in_rank_order)
+        buf = C.create_string_buffer(data, len(data))
+        self._ck(self.lib.flip_dist_p2p_import(self.h, buf))
+
     # ---- params / stats ----
     def set_param(self, name, value):
         self._ck(self.lib.flip_set_param(self.h, name.encode(), C.c_double(value)))

@@ -143,6 +143,13 @@ int flip_get_stats(flip_sim *h, flip_stats *out);
  * particle/grid stages run replicated (multi-GPU). */
 int flip_dist_unique_id(void *out128);
 int flip_dist_init(flip_sim *h, int rank, int nranks, const void *unique_id128);
+/* Optional, after flip_dist_init: map the other ranks' exchange buffers (CUDA IPC) so that the per-
+ * iteration reductions and halo planes go through peer memory over NVLink instead of NCCL.  Every
+ * rank exports flip_dist_p2p_blob_size() bytes; the caller concatenates them in rank order (e.g. with
+ * an all-gather) and hands the result to every rank's import. */
+int flip_dist_p2p_blob_size(void);
+int flip_dist_p2p_export(flip_sim *h, void *out);
+int flip_dist_p2p_import(flip_sim *h, const void *all_blobs_in_rank_order);
 
 /* pinned host buffers for callers that want asynchronous copies */
 int flip_host_alloc(void **ptr, uint64_t bytes);

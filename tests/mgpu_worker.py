@@ -25,6 +25,10 @@ def main():
     box = [sim.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     sim.dist_init(rank, world, box[0])
+    if os.environ.get("FLIP_P2P", "1") == "1":
+        blobs = [None] * world
+        dist.all_gather_object(blobs, sim.dist_p2p_export())
+        sim.dist_p2p_import(blobs)
     for _ in range(3):
         sim.advance(0.01)
     out = sim.get_particles()
