@@ -577,8 +577,7 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
             apply(parity);
             dist_reduce_partials(s, P.part, G, false);
             FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
-            dist_reduce_partials(s, P.part + G, G, false);
-            dist_reduce_partials(s, P.part + 2 * G, G, true);
+            dist_reduce_pair(s, P.part + G, P.part + 2 * G, G, nullptr, 0);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
         }
     };
@@ -796,6 +795,7 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
     dist_reduce_partials(s, P.part + 2 * G, G, true);
     // first CGState: reuses k_cg_begin (rho := gamma0, tolerance, trivial-rhs exits)
     FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, 0);
+    dist_halo_exchange(s, Q.P.z, NC);
     apply_uw(0);
     dist_reduce_partials(s, P.part, G, false);
     s.kernel_launches += 3;
@@ -805,8 +805,8 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;
             FLIP_LAUNCH_SYNC(kstep, G, CG_THREADS, s.stream, Q, diag, parity);
-            dist_reduce_partials(s, P.part + (parity ? 1 : 3) * G, G, false);
-            dist_reduce_partials(s, P.part + (parity ? 2 : 4) * G, G, true);
+            // gamma (sum), max|r| (max) and the ghost planes of u in ONE exchange
+            dist_reduce_pair(s, P.part + (parity ? 1 : 3) * G, P.part + (parity ? 2 : 4) * G, G, Q.P.z, NC);
             apply_uw(parity ^ 1);
             dist_reduce_partials(s, P.part, G, false);
         }

@@ -24,6 +24,7 @@ void dist_reduce_partials(Sim &, double *, int, bool) {}
 void dist_halo_exchange(Sim &, double *, int) {}
 void dist_allgather_slabs(Sim &, double *, int) {}
 void dist_allreduce_int(Sim &, int *) {}
+void dist_reduce_pair(Sim &, double *, double *, int, double *, int) {}
 #else
 #include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 #include <dlfcn.h>
@@ -148,6 +149,14 @@ void dist_reduce_partials(Sim &s, double *part, int n, bool is_max) {
     k_collapse_partials<<<1, 512, 0, s.stream>>>(part, n, is_max ? 1 : 0);
     s.kernel_launches++;
     NCCL_CHECK(ncclAllReduce(part, part, 1, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)s.nccl, s.stream));
+}
+
+void dist_reduce_pair(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp) {
+    if (s.nranks == 1) return;
+    if (dist_p2p_active(s)) { dist_p2p_step(s, part_sum, part_max, n, field, ncomp); return; }
+    dist_reduce_partials(s, part_sum, n, false);
+    dist_reduce_partials(s, part_max, n, true);
+    if (field) dist_halo_exchange(s, field, ncomp);
 }
 
 void dist_allreduce_int(Sim &s, int *dev_value) {

@@ -199,6 +199,105 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const double *__restrict__ fie
     }
 }
 
+
+// Fused exchange after a kernel that produced a sum partial, a max partial and new values of a
+// halo-exchanged field: halo copy by all CTAs; the last CTA reduces both partial arrays, posts them,
+// raises the halo flags and waits for everything.  One kernel instead of three.
+__global__ void __launch_bounds__(256) k_p2p_step(double *__restrict__ part_sum, double *__restrict__ part_max, int n,
+                                                  const double *__restrict__ field, double *lo_peer, double *hi_peer, int ncomp,
+                                                  size_t total, size_t pe, size_t off_first, size_t off_last, Mailbox *local,
+                                                  Mailbox **peers, Mailbox *lo_box, Mailbox *hi_box, int rank, int nranks) {
+    __shared__ double sm[2][8];
+    __shared__ int is_last;
+    if (field) {
+        size_t cnt = (size_t)ncomp * pe;
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += (size_t)gridDim.x * blockDim.x) {
+            size_t c = t / pe, e = t % pe;
+            if (lo_peer) lo_peer[c * total + off_first + e] = field[c * total + off_first + e];
+            if (hi_peer) hi_peer[c * total + off_last + e] = field[c * total + off_last + e];
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(&local->halo_done, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    // ---- last CTA ----
+    double vs = 0.0, vm = 0.0;
+    for (int q = threadIdx.x; q < n; q += 256) { vs += part_sum[q]; vm = fmax(vm, part_max[q]); }
+    for (int o = 16; o > 0; o >>= 1) {
+        vs += __shfl_xor_sync(0xffffffffu, vs, o);
+        vm = fmax(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+    }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = vs; sm[1][threadIdx.x >> 5] = vm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        local->halo_done = 0;
+        double rs = sm[0][0], rm = sm[1][0];
+        for (int w = 1; w < 8; w++) { rs += sm[0][w]; rm = fmax(rm, sm[1][w]); }
+        // two consecutive reduction sequence numbers: [sum, max]
+        unsigned long long seq = local->seq_reduce + 2;
+        local->seq_reduce = seq;
+        int s0 = (int)((seq - 1) & (P2P_SLOTS - 1)), s1 = (int)(seq & (P2P_SLOTS - 1));
+        for (int p = 0; p < nranks; p++) {
+            ((volatile double *)peers[p]->val[s0])[rank] = rs;
+            ((volatile double *)peers[p]->val[s1])[rank] = rm;
+        }
+        unsigned long long hseq = 0;
+        int hslot = 0;
+        if (field) { hseq = local->seq_halo + 1; local->seq_halo = hseq; hslot = (int)(hseq & (P2P_SLOTS - 1)); }
+        __threadfence_system();
+        for (int p = 0; p < nranks; p++) {
+            ((volatile unsigned long long *)peers[p]->flag[s0])[rank] = seq - 1;
+            ((volatile unsigned long long *)peers[p]->flag[s1])[rank] = seq;
+        }
+        if (field) {
+            if (lo_box) ((volatile unsigned long long *)lo_box->hflag[1])[hslot] = hseq;
+            if (hi_box) ((volatile unsigned long long *)hi_box->hflag[0])[hslot] = hseq;
+        }
+        double ts = 0.0, tm = 0.0;
+        for (int src = 0; src < nranks; src++) {
+            p2p_wait(&((volatile unsigned long long *)local->flag[s1])[src], seq, &local->status);   // s1 is posted after s0
+            __threadfence_system();
+            ts += ((volatile double *)local->val[s0])[src];
+            tm = fmax(tm, ((volatile double *)local->val[s1])[src]);
+        }
+        if (field) {
+            if (lo_box) p2p_wait(&((volatile unsigned long long *)local->hflag[0])[hslot], hseq, &local->status);
+            if (hi_box) p2p_wait(&((volatile unsigned long long *)local->hflag[1])[hslot], hseq, &local->status);
+            __threadfence_system();
+        }
+        sm[0][0] = ts; sm[1][0] = tm;
+    }
+    __syncthreads();
+    double ts = sm[0][0], tm = sm[1][0];
+    for (int q = threadIdx.x; q < n; q += 256) { part_sum[q] = (q == 0) ? ts : 0.0; part_max[q] = (q == 0) ? tm : 0.0; }
+}
+
+void dist_p2p_step(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp) {
+    P2PState *st = p2p_of(s);
+    const Grid &g = s.g;
+    size_t pe = (size_t)g.ax * g.ay;
+    int k0 = FLIP_B * s.bz0, k1 = FLIP_B * s.bz1;
+    size_t off_first = (size_t)(k0 + FLIP_PZ) * pe, off_last = (size_t)(k1 - 1 + FLIP_PZ) * pe;
+    double *lo = nullptr, *hi = nullptr;
+    if (field) {
+        int which = field == s.cg_s ? 0 : (field == s.cg_z ? 1 : -1);
+        if (which < 0) throw FlipError("p2p step: field is not one of the exported arrays");
+        lo = s.rank > 0 ? st->field_peer[which][s.rank - 1] : nullptr;
+        hi = s.rank < s.nranks - 1 ? st->field_peer[which][s.rank + 1] : nullptr;
+    }
+    Mailbox *lob = s.rank > 0 ? st->peer[s.rank - 1] : nullptr;
+    Mailbox *hib = s.rank < s.nranks - 1 ? st->peer[s.rank + 1] : nullptr;
+    int grid = field ? s.num_sms : 1;
+    k_p2p_step<<<grid, 256, 0, s.stream>>>(part_sum, part_max, n, (const double *)field, lo, hi, ncomp, (size_t)g.total, pe, off_first,
+                                           off_last, st->local, st->peer_dev, lob, hib, s.rank, s.nranks);
+    s.kernel_launches++;
+}
+
 void dist_p2p_reduce(Sim &s, double *part, int n, bool is_max) {
     P2PState *st = p2p_of(s);
     k_p2p_allreduce<<<1, 512, 0, s.stream>>>(part, n, is_max ? 1 : 0, st->local, st->peer_dev, s.rank, s.nranks);
@@ -231,4 +330,5 @@ bool dist_p2p_active(Sim &) { return false; }
 int dist_p2p_status(Sim &) { return 0; }
 void dist_p2p_reduce(Sim &, double *, int, bool) {}
 void dist_p2p_halo(Sim &, double *, int) {}
+void dist_p2p_step(Sim &, double *, double *, int, double *, int) {}
 #endif

@@ -133,7 +133,6 @@ void solve_pressure(Sim &s, float dt) {
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
         h = run_cg2<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, [&](int parity) {
-            dist_halo_exchange(s, Pu.s, 1);
             FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, Pu, coef, parity);
         }, 0);
     } else {

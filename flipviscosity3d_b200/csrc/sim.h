@@ -175,6 +175,9 @@ bool dist_p2p_active(Sim &s);
 int dist_p2p_status(Sim &s);
 void dist_p2p_reduce(Sim &s, double *part, int n, bool is_max);
 void dist_p2p_halo(Sim &s, double *field, int ncomp);
+void dist_p2p_step(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp);
+// sum partials + max partials (+ optional halo of `field`) in one exchange where peer memory is active
+void dist_reduce_pair(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp);
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);

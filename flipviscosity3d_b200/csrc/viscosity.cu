@@ -498,7 +498,6 @@ void stage_apply_viscosity(Sim &s, float dt) {
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
         h = run_cg2<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
-            dist_halo_exchange(s, Pu.s, 3);
             FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Pu, vcoef, vdiag, parity);
         }, 1);
     } else {
