@@ -1,0 +1,18 @@
+"""experiments: Galerkin MG variants (dev only)"""
+import sys, time
+import numpy as np
+sys.path.insert(0, "dev")
+from visc_proto import *
+st = np.load(sys.argv[1])
+L0 = make_level0(st)
+A, b = assemble(L0, with_rhs=True)
+d = A.diagonal()
+print(sys.argv[1], "unknowns", L0.nunk, flush=True)
+if "--nojac" not in sys.argv:
+    t0 = time.time(); x, it = pcg(A, b, lambda r: r / d); print("jacobi", it, "%.1fs" % (time.time() - t0), flush=True)
+for kw in [dict(galerkin=True), dict(galerkin=True, transverse="const"), dict(galerkin=True, transverse="const", alpha=1.5),
+           dict(galerkin=True, transverse="const", alpha=2.0), dict(galerkin=False)]:
+    t0 = time.time()
+    mg = MG(L0, A, verbose=False, **kw)
+    x, it = pcg(A, b, mg.vcycle, maxit=3000)
+    print(kw, "levels", len(mg.A), "nnz/row L1 %.0f" % (mg.A[1].nnz / mg.A[1].shape[0]), "iterations", it, "%.1fs" % (time.time() - t0), flush=True)

@@ -65,6 +65,7 @@ struct CGParams {
     double *part;              // [3*gridDim]: s.q | r.z | max|r|
     CGState *st;               // [2]
     int strict;                // 1: converged when max|r| < tol (pressure), 0: <= tol (viscosity)
+    int flexible;              // multigrid mode: Polak-Ribiere beta = -(q.z)/(s.q), robust to an inexact V-cycle
 };
 
 // diagonal accessors
@@ -230,17 +231,23 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
     if (parity >= 0 && P.st[parity].done) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
-    double rz = 0.0;
+    double rz = 0.0, qz = 0.0;
     for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
         int id = P.cell_list[qq];
         for (int m = 0; m < NC; m++) {
             if (diag(m, id) == 0.0f) continue;
             size_t o = (size_t)m * g.total + id;
-            rz += P.r[o] * P.z[o];
+            double z = P.z[o];
+            rz += P.r[o] * z;
+            if (P.flexible) qz += P.q[o] * z;
         }
     }
     rz = cta_reduce<false>(rz, sm);
-    if (threadIdx.x == 0) P.part[gridDim.x + blockIdx.x] = rz;
+    if (P.flexible) qz = cta_reduce<false>(qz, sm);
+    if (threadIdx.x == 0) {
+        P.part[gridDim.x + blockIdx.x] = rz;
+        if (P.flexible) P.part[3 * gridDim.x + blockIdx.x] = qz;
+    }
 }
 
 // multigrid mode, start-up: x = 0, r = masked b, partial max|b|   (then V-cycle, k_cg_dot, k_cg_start)
@@ -303,6 +310,12 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
     }
     if (conv || bad) return;
     double beta = rho_new / st.rho;
+    if (MG && P.flexible) {
+        // beta = z_new.(r_new - r_old) / rho_old with r_new - r_old = -alpha q and alpha = rho_old / s.q
+        double sq = reduce_partials<false>(P.part, gridDim.x, sm);
+        double qz = reduce_partials<false>(P.part + 3 * gridDim.x, gridDim.x, sm);
+        beta = -qz / sq;
+    }
     int nc = *P.cell_count;
     for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
         int id = P.cell_list[qq];
@@ -643,6 +656,7 @@ static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double t
         CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         h = *s.cgst_host;
+        if (s.verbose > 1) printf("\t\tmg-pcg iteration %d max|r| %.3e (tol %.3e)\n", h.iter, h.resid, h.tol), fflush(stdout);
         if (h.done || launched >= maxit + chunk) break;
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;

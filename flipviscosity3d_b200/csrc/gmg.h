@@ -1,0 +1,548 @@
+// Galerkin geometric multigrid: the preconditioner of the viscosity CG.
+//
+// The reference preconditions with MIC(0) (src/pcgsolver/pcgsolver.h:62-214), a sequential
+// recurrence that barely beats the diagonal on this coupled system (64^3: 364 vs 468 iterations)
+// and hits its 700-iteration cap from 128^3 up.  The rediscretised V-cycle of vmg.h
+// gains 5-13x; its weak point, measured on a scipy prototype of the same operator
+// (dev/visc_proto.py), is the coarse operator next to the free surface.  Here the coarse operators
+// are the exact Galerkin products  A_c = P^T A P / 8  with the staggered trilinear transfers of
+// vmg.h (linear along the face normal, cell-centred linear across it, renormalised at the free
+// surface): 20-25x fewer iterations than the diagonal at 64^3-128^3, and nothing to tune.
+//
+//   level 0       the solver's own matrix-free coupled stencil (k_visc_apply / vmg_row)
+//   levels >= 1   explicit windowed stencils.  A product of trilinear transfers with a 15-point
+//                 operator closes on a fixed window per (row component m, column component m'):
+//                 m == m': 3 x 5 x 5 (3 along the face normal), m != m': 4 x 4 x 5  ->  235 slots
+//                 per row on every level.  Stored row-major over a compact row list
+//                 (S[row * 240 + slot]); one WARP applies one row (coalesced 960-byte read, 8 slots
+//                 per lane, shuffle reduction), so even the 100-row levels finish in one memory
+//                 round trip.  Vectors stay in the dense padded layout: neighbours are plain offsets.
+//   set-up        one thread per (coarse row, column component) accumulates its <= 80 slots in
+//                 shared memory in a fixed order: no atomics, bit-reproducible.
+//   cycle         V(2,2), damped Jacobi, fp32 inside (the outer CG stays fp64), symmetric, so
+//                 plain CG remains valid.
+#pragma once
+#include "vmg.h"
+
+#define GMG_MAX_LEVELS 8
+#define GMG_SLOTS 235
+#define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
+#define GMG_BUILD_THREADS 64      // x 80 fp64 accumulators = 40 KB of shared memory
+
+struct GWin { int lo[3], n[3], base, size; };
+
+// window of column component mp inside a row of component m
+FLIP_HD GWin gmg_window(int m, int mp) {
+    GWin w;
+    w.base = 0;
+    for (int q = 0; q < mp; q++) w.base += (q == m) ? 75 : 80;
+    for (int a = 0; a < 3; a++) {
+        if (m == mp) { w.lo[a] = (a == m) ? -1 : -2; w.n[a] = (a == m) ? 3 : 5; }
+        else if (a == m) { w.lo[a] = -2; w.n[a] = 4; }
+        else if (a == mp) { w.lo[a] = -1; w.n[a] = 4; }
+        else { w.lo[a] = -2; w.n[a] = 5; }
+    }
+    w.size = w.n[0] * w.n[1] * w.n[2];
+    return w;
+}
+
+struct GLevel {
+    Grid g;
+    float *diag = 0;      // [3T] > 0 on unknowns (level 0: the solver's vdiag; else Galerkin diagonal)
+    float *pn = 0;        // [3T] sum of the prolongation weights of a face's coarse parents that exist
+    float *x[2] = {0, 0}, *b = 0, *r = 0;   // [3T]
+    int *blk_flag = 0, *blk_list = 0, *blk_count = 0;
+    int *rows = 0;        // [nrows] m*T + id, grouped by block, component-major inside a block
+    int *rowmap = 0;      // [3T] inverse of rows (-1 = not an unknown)
+    int *nrows_dev = 0;
+    int nrows = 0;
+    size_t cap = 0;       // rows S is allocated for
+    float *S = 0;         // [nrows * GMG_STRIDE]
+    float *wj = 0;        // [nrows] smoothing weight per row
+    bool owns = false;
+};
+
+struct GMG {
+    int nlevels = 0, nalloc = 0;
+    GLevel lv[GMG_MAX_LEVELS];
+    int pre = 2, coarse_sweeps = 24;
+    float omega = 0.5f;
+    int *count_host = 0;  // pinned
+};
+
+struct GLevelDev {
+    Grid g;
+    const float *diag;
+    const int *rows;
+    const int *nrows;
+    const float *S;
+    const float *wj;     // [nrows] smoothing weights
+};
+
+FLIP_D void gmg_unflatten(const Grid &g, int id, int &i, int &j, int &k) {
+    int x = id % g.ax, r = id / g.ax;
+    i = x - FLIP_PX; j = (r % g.ay) - FLIP_PY; k = (r / g.ay) - FLIP_PZ;
+}
+
+// coarse unknown flags: a coarse face is an unknown if one of its nearest fine faces is one
+__global__ void __launch_bounds__(256) k_gmg_flags(Grid gc, Grid gf, const float *__restrict__ diag_f, float *__restrict__ diag_c) {
+    int I, J, K;
+    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, gc.ni + 1, gc.nj + 1, gc.nk + 1, I, J, K)) return;
+    size_t Tf = (size_t)gf.total, Tc = (size_t)gc.total;
+    int id = gidx(gc, I, J, K);
+    bool interior = I >= 1 && I < gc.ni && J >= 1 && J < gc.nj && K >= 1 && K < gc.nk;
+    for (int m = 0; m < 3; m++) {
+        bool any = false;
+        if (interior)
+            for (int a = (m == 0 ? -1 : 0); a <= 1 && !any; a++)
+                for (int b = (m == 1 ? -1 : 0); b <= 1 && !any; b++)
+                    for (int c = (m == 2 ? -1 : 0); c <= 1; c++) {
+                        int fi = 2 * I + a, fj = 2 * J + b, fk = 2 * K + c;
+                        if (fi < 0 || fj < 0 || fk < 0 || fi > gf.ni || fj > gf.nj || fk > gf.nk) continue;
+                        if (diag_f[m * Tf + gidx(gf, fi, fj, fk)] != 0.0f) { any = true; break; }
+                    }
+        diag_c[m * Tc + id] = any ? 1.0f : 0.0f;
+    }
+}
+
+// rows of a level: per active block, component-major
+__global__ void __launch_bounds__(CG_THREADS) k_gmg_row_counts(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                                const float *__restrict__ diag, int *__restrict__ per_block) {
+    __shared__ int wsum[CG_THREADS / 32];
+    int nb = *count;
+    size_t T = (size_t)g.total;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        int n = 0;
+        if (c.inside) {
+            int id = gidx(g, c.i, c.j, c.k);
+            for (int m = 0; m < 3; m++) n += diag[m * T + id] != 0.0f ? 1 : 0;
+        }
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < CG_THREADS / 32; w++) t += wsum[w];
+            per_block[b] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                              const float *__restrict__ diag, const int *__restrict__ offset,
+                                                              int *__restrict__ rows, int *__restrict__ rowmap) {
+    __shared__ int wsum[CG_THREADS / 32];
+    int nb = *count;
+    size_t T = (size_t)g.total;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        int id = c.inside ? gidx(g, c.i, c.j, c.k) : 0;
+        int base = offset[b];
+        for (int m = 0; m < 3; m++) {
+            bool has = c.inside && diag[m * T + id] != 0.0f;
+            unsigned bal = __ballot_sync(0xffffffffu, has);
+            __syncthreads();
+            if (lane == 0) wsum[wid] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < CG_THREADS / 32; w++) { if (w < wid) before += wsum[w]; total += wsum[w]; }
+            if (has) {
+                int r = base + before + __popc(bal & ((1u << lane) - 1u));
+                rows[r] = (int)(m * T + id);
+                rowmap[m * T + id] = r;
+            }
+            base += total;
+        }
+    }
+}
+
+// pn: prolongation normaliser of every unknown of the fine level
+__global__ void __launch_bounds__(CG_THREADS) k_gmg_pnorm(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                           const float *__restrict__ diag, Grid gc, const float *__restrict__ diag_c,
+                                                           float *__restrict__ pn) {
+    int nb = *count;
+    size_t T = (size_t)g.total;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        if (!c.inside) continue;
+        int id = gidx(g, c.i, c.j, c.k);
+        for (int m = 0; m < 3; m++)
+            pn[m * T + id] = diag[m * T + id] != 0.0f ? vmg_pnorm(m, c.i, c.j, c.k, gc, diag_c) : 0.0f;
+    }
+}
+
+// --- fine-operator entry enumeration ---------------------------------------------------------
+// level 0: the <= 7 entries of row (m, id) whose column component is mp (csrc/viscosity.cu k_visc_apply)
+FLIP_D int gmg_entries_l0(int m, int mp, int id, int sy, int sz, size_t T, const float *__restrict__ coef,
+                          const float *__restrict__ diag, int off[7][3], float val[7]) {
+    const float *cc = coef, *cu = coef + T, *cv = coef + 2 * T, *cw = coef + 3 * T;
+    float fR, fL, fT, fB, fF, fK;
+    if (m == 0) { fR = cc[id]; fL = cc[id - 1]; fT = cw[id + sy]; fB = cw[id]; fF = cv[id + sz]; fK = cv[id]; }
+    else if (m == 1) { fR = cw[id + 1]; fL = cw[id]; fT = cc[id]; fB = cc[id - sy]; fF = cu[id + sz]; fK = cu[id]; }
+    else { fR = cv[id + 1]; fL = cv[id]; fT = cu[id + sy]; fB = cu[id]; fF = cc[id]; fK = cc[id - sz]; }
+    int n = 0;
+#define GMG_E(di, dj, dk, v) { off[n][0] = di; off[n][1] = dj; off[n][2] = dk; val[n] = v; n++; }
+    if (m == mp) {
+        GMG_E(0, 0, 0, diag[m * T + id]) GMG_E(1, 0, 0, -fR) GMG_E(-1, 0, 0, -fL) GMG_E(0, 1, 0, -fT) GMG_E(0, -1, 0, -fB)
+        GMG_E(0, 0, 1, -fF) GMG_E(0, 0, -1, -fK)
+    } else if (m == 0 && mp == 1) { GMG_E(0, 1, 0, -fT) GMG_E(-1, 1, 0, fT) GMG_E(0, 0, 0, fB) GMG_E(-1, 0, 0, -fB) }
+    else if (m == 0 && mp == 2) { GMG_E(0, 0, 1, -fF) GMG_E(-1, 0, 1, fF) GMG_E(0, 0, 0, fK) GMG_E(-1, 0, 0, -fK) }
+    else if (m == 1 && mp == 0) { GMG_E(1, 0, 0, -fR) GMG_E(1, -1, 0, fR) GMG_E(0, 0, 0, fL) GMG_E(0, -1, 0, -fL) }
+    else if (m == 1 && mp == 2) { GMG_E(0, 0, 1, -fF) GMG_E(0, -1, 1, fF) GMG_E(0, 0, 0, fK) GMG_E(0, -1, 0, -fK) }
+    else if (m == 2 && mp == 0) { GMG_E(1, 0, 0, -fR) GMG_E(1, 0, -1, fR) GMG_E(0, 0, 0, fL) GMG_E(0, 0, -1, -fL) }
+    else { GMG_E(0, 1, 0, -fT) GMG_E(0, 1, -1, fT) GMG_E(0, 0, 0, fB) GMG_E(0, 0, -1, -fB) }
+#undef GMG_E
+    return n;
+}
+
+// scatter one fine entry (row weight wP, value a, column (mp; ji,jj,jk)) to the coarse parents of the column
+FLIP_D void gmg_scatter(double (*acc)[GMG_BUILD_THREADS], const GWin &W, int mp, double wa, int ji, int jj, int jk, int I, int J, int K,
+                        const Grid &gc, const float *__restrict__ diag_c) {
+    int pi[2], pj[2], pk[2];
+    float wi[2], wj[2], wk[2];
+    vmg_parents(mp == 0, ji, pi[0], pi[1], wi[0], wi[1]);
+    vmg_parents(mp == 1, jj, pj[0], pj[1], wj[0], wj[1]);
+    vmg_parents(mp == 2, jk, pk[0], pk[1], wk[0], wk[1]);
+    const float *d = diag_c + (size_t)mp * gc.total;
+    for (int c2 = 0; c2 < 2; c2++)
+        for (int b2 = 0; b2 < 2; b2++)
+            for (int a = 0; a < 2; a++) {
+                float w = wi[a] * wj[b2] * wk[c2];
+                if (w == 0.0f) continue;
+                int PI = pi[a], PJ = pj[b2], PK = pk[c2];
+                if (PI < 0 || PJ < 0 || PK < 0 || PI > gc.ni || PJ > gc.nj || PK > gc.nk) continue;
+                if (d[gidx(gc, PI, PJ, PK)] == 0.0f) continue;
+                int oi = PI - I - W.lo[0], oj = PJ - J - W.lo[1], ok = PK - K - W.lo[2];
+                if (oi < 0 || oj < 0 || ok < 0 || oi >= W.n[0] || oj >= W.n[1] || ok >= W.n[2]) continue;  // cannot happen
+                acc[(ok * W.n[1] + oj) * W.n[0] + oi][threadIdx.x] += wa * (double)w;
+            }
+}
+
+// A_c = P^T A P / 8.  One thread per (coarse row, column component); grid = 3 * ceil(nrows / 128).
+// FINE0: the fine level is level 0 (matrix-free coefficients), else an explicit stencil level.
+template <bool FINE0>
+__global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, int nrows_c,
+                                                                  const float *__restrict__ diag_c, float *__restrict__ S_c,
+                                                                  const float *__restrict__ diag_f, const float *__restrict__ pn_f,
+                                                                  const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
+                                                                  const float *__restrict__ S_f, int nrows_f) {
+    // fp64 accumulation: the mass term of a coarse row (its row sum, ~1) is what remains of ~5000 products of size
+    // ~1e4 that cancel; in fp32 it came out with O(1) relative error at 256^3, the near-rigid coarse modes lost
+    // their (tiny, positive) energy and the V-cycle stopped being positive definite.
+    __shared__ double acc[80][GMG_BUILD_THREADS];
+    const int mp = blockIdx.x % 3;
+    const int r = (blockIdx.x / 3) * GMG_BUILD_THREADS + threadIdx.x;
+    if (r >= nrows_c) return;
+    const size_t Tc = (size_t)gc.total, Tf = (size_t)gf.total;
+    const int enc = rows_c[r];
+    const int m = enc / (int)Tc, idc = enc - m * (int)Tc;
+    int I, J, K;
+    gmg_unflatten(gc, idc, I, J, K);
+    const GWin W = gmg_window(m, mp);
+    for (int q = 0; q < W.size; q++) acc[q][threadIdx.x] = 0.0;
+    const int sy = SY(gf), sz = SZ(gf);
+    int li, ci, lj, cj, lk, ck;
+    float wi[4], wj[4], wk[4];
+    vmg_axis(m == 0, I, li, ci, wi);
+    vmg_axis(m == 1, J, lj, cj, wj);
+    vmg_axis(m == 2, K, lk, ck, wk);
+    for (int c2 = 0; c2 < ck; c2++) {
+        int fk = lk + c2;
+        if (fk < 0 || fk > gf.nk) continue;
+        for (int b2 = 0; b2 < cj; b2++) {
+            int fj = lj + b2;
+            if (fj < 0 || fj > gf.nj) continue;
+            for (int a = 0; a < ci; a++) {
+                int fi = li + a;
+                if (fi < 0 || fi > gf.ni) continue;
+                int idf = gidx(gf, fi, fj, fk);
+                if (diag_f[m * Tf + idf] == 0.0f) continue;
+                float pnf = pn_f[m * Tf + idf];
+                if (pnf == 0.0f) continue;
+                double wP = (double)(wi[a] * wj[b2] * wk[c2]) / (double)pnf;
+                if (FINE0) {
+                    int off[7][3];
+                    float val[7];
+                    int ne = gmg_entries_l0(m, mp, idf, sy, sz, Tf, coef_f, diag_f, off, val);
+                    for (int e = 0; e < ne; e++) {
+                        int ji = fi + off[e][0], jj = fj + off[e][1], jk = fk + off[e][2];
+                        size_t oj = mp * Tf + idf + off[e][0] + off[e][1] * sy + off[e][2] * sz;
+                        if (diag_f[oj] == 0.0f) continue;         // column is not an unknown: entry dropped
+                        float pnj = pn_f[oj];
+                        if (pnj == 0.0f) continue;
+                        gmg_scatter(acc, W, mp, wP * (double)val[e] / (double)pnj, ji, jj, jk, I, J, K, gc, diag_c);
+                    }
+                } else {
+                    int rf = rowmap_f[m * Tf + idf];
+                    const GWin F = gmg_window(m, mp);
+                    int slot = F.base;
+                    for (int dk = F.lo[2]; dk < F.lo[2] + F.n[2]; dk++)
+                        for (int dj = F.lo[1]; dj < F.lo[1] + F.n[1]; dj++)
+                            for (int di = F.lo[0]; di < F.lo[0] + F.n[0]; di++, slot++) {
+                                float v = S_f[(size_t)rf * GMG_STRIDE + slot];
+                                if (v == 0.0f) continue;
+                                size_t oj = mp * Tf + idf + di + dj * sy + dk * sz;
+                                float pnj = pn_f[oj];
+                                if (pnj == 0.0f) continue;
+                                gmg_scatter(acc, W, mp, wP * (double)v / (double)pnj, fi + di, fj + dj, fk + dk, I, J, K, gc, diag_c);
+                            }
+                }
+            }
+        }
+    }
+    for (int q = 0; q < W.size; q++) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q][threadIdx.x]);
+}
+
+// dense diagonal of an explicit level (also its unknown flag) = the (0,0,0) slot of the (m,m) window, and the
+// per-row smoothing weight  w = min(omega / a_ii, GMG_L1_BOUND / sum_j |a_ij|).  Galerkin rows next to the free
+// surface can have sum|a_ij| / a_ii >> 2, and lambda_max(D^-1 A_c) was measured at 3.3 - 4.3 on the coarse levels:
+// plain damped Jacobi with omega = 0.5 then amplifies a few modes (omega * lambda > 2), the V-cycle turns
+// indefinite and CG wanders for hundreds of iterations.  With the l1 cap, lambda_max(W A_c) <= GMG_L1_BOUND < 2
+// by Gershgorin, for any geometry.  One warp per row.
+#define GMG_L1_BOUND 1.6f
+__global__ void __launch_bounds__(256) k_gmg_diag(Grid g, const int *__restrict__ rows, int nrows, const float *__restrict__ S,
+                                                   float *__restrict__ diag, float *__restrict__ wj, float omega) {
+    int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    int enc = rows[r];
+    int m = enc / g.total;
+    GWin W = gmg_window(m, m);
+    int dslot = W.base + ((-W.lo[2]) * W.n[1] + (-W.lo[1])) * W.n[0] + (-W.lo[0]);
+    const float *Sr = S + (size_t)r * GMG_STRIDE;
+    float l1 = 0.0f;
+    for (int q = lane; q < GMG_SLOTS; q += 32) l1 += fabsf(Sr[q]);
+    for (int o = 16; o > 0; o >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    if (lane == 0) {
+        float d = Sr[dslot];
+        diag[enc] = d > 1e-30f ? d : 1e-30f;   // stays an unknown; a degenerate row is simply not smoothed
+        float w = d > 1e-20f ? omega / d : 0.0f;
+        if (l1 > 0.0f) w = fminf(w, GMG_L1_BOUND / l1);
+        wj[r] = w;
+    }
+}
+
+// offset (in elements, column component included) of slot `slot` of a row of component m; 0 for padding
+FLIP_HD int gmg_slot_offset(const Grid &g, int m, int slot) {
+    for (int mp = 0; mp < 3; mp++) {
+        GWin W = gmg_window(m, mp);
+        if (slot < W.base + W.size) {
+            int q = slot - W.base;
+            int di = W.lo[0] + q % W.n[0], dj = W.lo[1] + (q / W.n[0]) % W.n[1], dk = W.lo[2] + q / (W.n[0] * W.n[1]);
+            return mp * g.total + di + dj * SY(g) + dk * SZ(g);
+        }
+    }
+    return 0;
+}
+
+// One warp per row.  mode 0: xo = omega b / d (first sweep from zero)   1: xo = xi + omega (b - A xi) / d
+// 2: ro = (b - A xi) / pn  (residual, pre-scaled for the restriction)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__restrict__ b, const float *__restrict__ xi,
+                                                    float *__restrict__ out, const float *__restrict__ pn, float omega,
+                                                    const CGState *__restrict__ st) {
+    __shared__ int offs[3][GMG_STRIDE];
+    if (st && st->done) return;
+    if (MODE != 0) {
+        for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) {
+            int m = q / GMG_STRIDE, slot = q - m * GMG_STRIDE;
+            offs[m][slot] = slot < GMG_SLOTS ? gmg_slot_offset(L.g, m, slot) : 0;
+        }
+        __syncthreads();
+    }
+    const int nrows = *L.nrows;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+        int enc = L.rows[r];
+        int m = enc / L.g.total, id = enc - m * L.g.total;
+        if (MODE == 0) {
+            if (lane == 0) out[enc] = L.wj[r] * b[enc];
+            continue;
+        }
+        const float *__restrict__ Sr = L.S + (size_t)r * GMG_STRIDE;
+        const float *__restrict__ xc = xi + id;
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            int slot = lane + 32 * t;
+            if (slot < GMG_STRIDE) acc += Sr[slot] * xc[offs[m][slot]];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
+            else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
+        }
+    }
+}
+
+// ---- level 0 on the solver's compact cell list ------------------------------------------------
+// Same loads as k_visc_apply (viscosity.cu), in fp32: one thread per cell index that holds an unknown,
+// all three face rows at once.  MODE 0: x = omega b / d.  1: x = xi + omega (b - A xi) / d.
+// 2: r = (b - A xi) / pn (residual, pre-scaled for the restriction).  3: like 1, and the result is the
+// preconditioned residual z handed back to the CG in fp64.
+struct G0Params {
+    Grid g;
+    const int *cell_list, *cell_count;
+    const float *coef, *diag, *pn;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__restrict__ b, const float *__restrict__ xi,
+                                                     float *__restrict__ out, double *__restrict__ zout, float omega,
+                                                     const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    const Grid &g = L.g;
+    const int sy = SY(g), sz = SZ(g);
+    const size_t T = (size_t)g.total;
+    const float *__restrict__ cc = L.coef, *__restrict__ cu = L.coef + T, *__restrict__ cv = L.coef + 2 * T, *__restrict__ cw = L.coef + 3 * T;
+    const int nc = *L.cell_count;
+    for (int qq = blockIdx.x * blockDim.x + threadIdx.x; qq < nc; qq += gridDim.x * blockDim.x) {
+        const int id = L.cell_list[qq];
+        const float dU = L.diag[id], dV = L.diag[T + id], dW = L.diag[2 * T + id];
+        const float bU = (float)b[id], bV = (float)b[T + id], bW = (float)b[2 * T + id];
+        if (MODE == 0) {
+            if (dU != 0.0f) out[id] = omega * bU / dU;
+            if (dV != 0.0f) out[T + id] = omega * bV / dV;
+            if (dW != 0.0f) out[2 * T + id] = omega * bW / dW;
+            continue;
+        }
+        const float *__restrict__ su = xi, *__restrict__ sv = xi + T, *__restrict__ sw = xi + 2 * T;
+        const float u0 = su[id], u_xp = su[id + 1], u_xm = su[id - 1], u_yp = su[id + sy], u_ym = su[id - sy],
+                    u_zp = su[id + sz], u_zm = su[id - sz], u_xp_ym = su[id + 1 - sy], u_xp_zm = su[id + 1 - sz];
+        const float v0 = sv[id], v_xp = sv[id + 1], v_xm = sv[id - 1], v_yp = sv[id + sy], v_ym = sv[id - sy],
+                    v_zp = sv[id + sz], v_zm = sv[id - sz], v_xm_yp = sv[id - 1 + sy], v_yp_zm = sv[id + sy - sz];
+        const float w0 = sw[id], w_xp = sw[id + 1], w_xm = sw[id - 1], w_yp = sw[id + sy], w_ym = sw[id - sy],
+                    w_zp = sw[id + sz], w_zm = sw[id - sz], w_xm_zp = sw[id - 1 + sz], w_ym_zp = sw[id - sy + sz];
+        const float c0 = cc[id], c_xm = cc[id - 1], c_ym = cc[id - sy], c_zm = cc[id - sz];
+        const float eu0 = cu[id], eu_yp = cu[id + sy], eu_zp = cu[id + sz];
+        const float ev0 = cv[id], ev_xp = cv[id + 1], ev_zp = cv[id + sz];
+        const float ew0 = cw[id], ew_xp = cw[id + 1], ew_yp = cw[id + sy];
+        float aU = 0.0f, aV = 0.0f, aW = 0.0f;
+        if (dU != 0.0f) {
+            const float fR = c0, fL = c_xm, fT = ew_yp, fB = ew0, fF = ev_zp, fK = ev0;
+            aU = dU * u0 - fR * u_xp - fL * u_xm - fT * u_yp - fB * u_ym - fF * u_zp - fK * u_zm - fT * v_yp + fT * v_xm_yp +
+                 fB * v0 - fB * v_xm - fF * w_zp + fF * w_xm_zp + fK * w0 - fK * w_xm;
+        }
+        if (dV != 0.0f) {
+            const float fR = ew_xp, fL = ew0, fT = c0, fB = c_ym, fF = eu_zp, fK = eu0;
+            aV = dV * v0 - fR * v_xp - fL * v_xm - fT * v_yp - fB * v_ym - fF * v_zp - fK * v_zm - fR * u_xp + fR * u_xp_ym +
+                 fL * u0 - fL * u_ym - fF * w_zp + fF * w_ym_zp + fK * w0 - fK * w_ym;
+        }
+        if (dW != 0.0f) {
+            const float fR = ev_xp, fL = ev0, fT = eu_yp, fB = eu0, fF = c0, fK = c_zm;
+            aW = dW * w0 - fR * w_xp - fL * w_xm - fT * w_yp - fB * w_ym - fF * w_zp - fK * w_zm - fR * u_xp + fR * u_xp_zm +
+                 fL * u0 - fL * u_zm - fT * v_yp + fT * v_yp_zm + fB * v0 - fB * v_zm;
+        }
+        if (MODE == 2) {
+            const float pU = L.pn[id], pV = L.pn[T + id], pW = L.pn[2 * T + id];
+            if (dU != 0.0f) out[id] = pU > 0.0f ? (bU - aU) / pU : 0.0f;
+            if (dV != 0.0f) out[T + id] = pV > 0.0f ? (bV - aV) / pV : 0.0f;
+            if (dW != 0.0f) out[2 * T + id] = pW > 0.0f ? (bW - aW) / pW : 0.0f;
+        } else {
+            const float xU = dU != 0.0f ? u0 + omega * (bU - aU) / dU : 0.0f;
+            const float xV = dV != 0.0f ? v0 + omega * (bV - aV) / dV : 0.0f;
+            const float xW = dW != 0.0f ? w0 + omega * (bW - aW) / dW : 0.0f;
+            if (MODE == 3) { zout[id] = (double)xU; zout[T + id] = (double)xV; zout[2 * T + id] = (double)xW; }
+            else {
+                if (dU != 0.0f) out[id] = xU;
+                if (dV != 0.0f) out[T + id] = xV;
+                if (dW != 0.0f) out[2 * T + id] = xW;
+            }
+        }
+    }
+}
+
+// value of the coarse correction P x_c at fine face (m; i,j,k), not yet divided by pn
+FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float *__restrict__ xc) {
+    int pi[2], pj[2], pk[2];
+    float wi[2], wj[2], wk[2];
+    vmg_parents(m == 0, i, pi[0], pi[1], wi[0], wi[1]);
+    vmg_parents(m == 1, j, pj[0], pj[1], wj[0], wj[1]);
+    vmg_parents(m == 2, k, pk[0], pk[1], wk[0], wk[1]);
+    const float *x = xc + (size_t)m * gc.total;
+    float v = 0.0f;
+    for (int c2 = 0; c2 < 2; c2++)
+        for (int b2 = 0; b2 < 2; b2++)
+            for (int a = 0; a < 2; a++) {
+                float w = wi[a] * wj[b2] * wk[c2];
+                if (w == 0.0f) continue;
+                int I = pi[a], J = pj[b2], K = pk[c2];
+                if (I < 0 || J < 0 || K < 0 || I > gc.ni || J > gc.nj || K > gc.nk) continue;
+                v += w * x[gidx(gc, I, J, K)];   // x_c is exactly 0 where the coarse face is not an unknown
+            }
+    return v;
+}
+
+// level 0: x += P x_c on the cell list
+__global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const float *__restrict__ xc, float *__restrict__ xf,
+                                                       const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    const Grid &g = F.g;
+    const size_t T = (size_t)g.total;
+    const int nc = *F.cell_count;
+    for (int qq = blockIdx.x * blockDim.x + threadIdx.x; qq < nc; qq += gridDim.x * blockDim.x) {
+        const int id = F.cell_list[qq];
+        int i, j, k;
+        gmg_unflatten(g, id, i, j, k);
+        for (int m = 0; m < 3; m++) {
+            float p = F.pn[m * T + id];
+            if (p > 0.0f) xf[m * T + id] += gmg_interp(m, i, j, k, gc, xc) / p;
+        }
+    }
+}
+
+// explicit levels: x += P x_c, one thread per fine row
+__global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *__restrict__ pn, Grid gc, const float *__restrict__ xc,
+                                                      float *__restrict__ xf, const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    const int nrows = *F.nrows;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        int enc = F.rows[r];
+        int m = enc / F.g.total, id = enc - m * F.g.total;
+        float p = pn[enc];
+        if (p <= 0.0f) continue;
+        int i, j, k;
+        gmg_unflatten(F.g, id, i, j, k);
+        xf[enc] += gmg_interp(m, i, j, k, gc, xc) / p;
+    }
+}
+
+// coarse b = P^T r / 8 (r already divided by pn) and the first sweep from zero, x0 = w b; one thread per coarse row
+__global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
+                                                             float *__restrict__ x0, const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    const int nrows = *C.nrows;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        int enc = C.rows[r];
+        int m = enc / C.g.total, id = enc - m * C.g.total;
+        int I, J, K;
+        gmg_unflatten(C.g, id, I, J, K);
+        const float *rr = rf + (size_t)m * gf.total;
+        int li, ci, lj, cj, lk, ck;
+        float wi[4], wj[4], wk[4];
+        vmg_axis(m == 0, I, li, ci, wi);
+        vmg_axis(m == 1, J, lj, cj, wj);
+        vmg_axis(m == 2, K, lk, ck, wk);
+        float acc = 0.0f;
+        for (int c2 = 0; c2 < ck; c2++) {
+            int fk = lk + c2;
+            if (fk < 0 || fk > gf.nk) continue;
+            for (int b2 = 0; b2 < cj; b2++) {
+                int fj = lj + b2;
+                if (fj < 0 || fj > gf.nj) continue;
+                float wjk = wj[b2] * wk[c2];
+                for (int a = 0; a < ci; a++) {
+                    int fi = li + a;
+                    if (fi < 0 || fi > gf.ni) continue;
+                    acc += wi[a] * wjk * rr[gidx(gf, fi, fj, fk)];
+                }
+            }
+        }
+        float bv = 0.125f * acc;
+        bc[enc] = bv;
+        x0[enc] = C.wj[r] * bv;
+    }
+}

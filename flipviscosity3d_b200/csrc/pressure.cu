@@ -121,7 +121,7 @@ void solve_pressure(Sim &s, float dt) {
     CGParams P;
     P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
     P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
-    P.part = s.part; P.st = s.cgst; P.strict = 1;
+    P.part = s.part; P.st = s.cgst; P.strict = 1; P.flexible = 0;
     int G = cg_grid(s);
     const float4 *coef = s.pcoef;
     cudaStream_t st = s.stream;

@@ -53,6 +53,8 @@ struct Sim {
     int mg_prune = 0;                   // 1: drop coarse strain terms that touch air faces (made it worse: off)
     float mg_alpha = 1.0f;              // scale of the coarse-grid correction
     int mg_levels = 8;                  // cap on the number of levels
+    int mg_chunk = 8;                   // multigrid CG iterations per graph replay / host convergence poll
+    int mg_flexible = 1;                // Polak-Ribiere beta in the multigrid-preconditioned CG
     int cg_chunk = 32;
     // 0 = textbook PCG (3 kernels, 2 reduction points per iteration), 1 = single-reduction
     // Chronopoulos-Gear recurrences (2 kernels).  Measured on B200 at 256^3: the fused update kernel wins
@@ -99,6 +101,7 @@ struct Sim {
     double *cg_z = 0;         // [3*total] preconditioned residual (multigrid mode; u = M^-1 r in the single-reduction CG)
     double *cg_w = 0;         // [3*total] w = A u (single-reduction CG)
     void *vmg = 0;            // viscosity multigrid hierarchy (VMG*, viscosity.cu)
+    void *gmg = 0;            // Galerkin multigrid hierarchy (GMG*, gmg.h / viscosity.cu)
     float *vvol = 0;          // 7 volume grids [7*total]: center,U,V,W,edgeU,edgeV,edgeW
     float *vnode = 0;         // 7 nodal phi grids [7*total]
     unsigned char *vvalid = 0;// dilated liquid mask

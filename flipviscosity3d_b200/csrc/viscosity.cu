@@ -14,7 +14,7 @@
 // masks are not needed: the search direction is kept at exactly 0 on non-unknown faces, which is
 // what the reference's "drop FLUID neighbours without an index, move SOLID neighbours to the rhs"
 // amounts to inside A*s.
-#include "vmg.h"
+#include "gmg.h"
 #include "levelset_math.h"
 
 // volume grid ids
@@ -338,7 +338,9 @@ static VMG *vmg_get(Sim &s) {
     return M;
 }
 
+static void gmg_free(Sim &s);
 void viscosity_free(Sim &s) {
+    gmg_free(s);
     VMG *M = (VMG *)s.vmg;
     if (!M) return;
     for (int l = 0; l < M->nalloc; l++) {
@@ -445,6 +447,276 @@ static void vmg_vcycle(Sim &s, VMG &M, const double *r_in, double *z_out, const 
     s.kernel_launches++;
 }
 
+// ------------------------------------------------------------------------------------------
+// Galerkin multigrid hierarchy (gmg.h): allocation, per-solve set-up, V-cycle launcher
+// ------------------------------------------------------------------------------------------
+static GMG *gmg_get(Sim &s) {
+    if (s.gmg) return (GMG *)s.gmg;
+    GMG *M = new GMG();
+    s.gmg = M;
+    CUDA_CHECK(cudaMallocHost((void **)&M->count_host, 4 * sizeof(int)));
+    Grid g = s.g;
+    for (int l = 0; l < GMG_MAX_LEVELS; l++) {
+        GLevel &L = M->lv[l];
+        L.g = g;
+        size_t T = (size_t)g.total;
+        vmg_dev_alloc(L.x[0], 3 * T);
+        vmg_dev_alloc(L.x[1], 3 * T);
+        vmg_dev_alloc(L.r, 3 * T);
+        vmg_dev_alloc(L.pn, 3 * T);
+        if (l == 0) {
+            L.diag = s.vdiag; L.blk_flag = s.blk_flag; L.blk_list = s.blk_list; L.blk_count = s.blk_count;
+            L.owns = false;
+        } else {
+            vmg_dev_alloc(L.diag, 3 * T); vmg_dev_alloc(L.b, 3 * T);
+            vmg_dev_alloc(L.blk_flag, (size_t)g.nblocks); vmg_dev_alloc(L.blk_list, (size_t)g.nblocks);
+            vmg_dev_alloc(L.blk_count, 1);
+            vmg_dev_alloc(L.rows, 3 * T); vmg_dev_alloc(L.rowmap, 3 * T); vmg_dev_alloc(L.nrows_dev, 1);
+            L.owns = true;
+        }
+        M->nalloc = l + 1;
+        int mn = g.ni < g.nj ? g.ni : g.nj;
+        mn = mn < g.nk ? mn : g.nk;
+        if (mn <= 4) break;
+        g = make_grid((g.ni + 1) / 2, (g.nj + 1) / 2, (g.nk + 1) / 2, g.dx * 2.0f);
+    }
+    return M;
+}
+
+static void gmg_free(Sim &s) {
+    GMG *M = (GMG *)s.gmg;
+    if (!M) return;
+    for (int l = 0; l < M->nalloc; l++) {
+        GLevel &L = M->lv[l];
+        cudaFree(L.x[0]); cudaFree(L.x[1]); cudaFree(L.r); cudaFree(L.pn);
+        if (L.owns) {
+            cudaFree(L.diag); cudaFree(L.b); cudaFree(L.blk_flag); cudaFree(L.blk_list); cudaFree(L.blk_count);
+            cudaFree(L.rows); cudaFree(L.rowmap); cudaFree(L.nrows_dev); cudaFree(L.S); cudaFree(L.wj);
+        }
+    }
+    cudaFreeHost(M->count_host);
+    delete M;
+    s.gmg = nullptr;
+}
+
+static GLevelDev gmg_dev(const GLevel &L) {
+    GLevelDev d;
+    d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj;
+    return d;
+}
+static VLevelDev gmg_vdev(const GLevel &L, const float *coef) {
+    VLevelDev d;
+    d.g = L.g; d.coef = coef; d.diag = L.diag; d.blk_list = L.blk_list; d.blk_count = L.blk_count;
+    return d;
+}
+static int gmg_grid(const Sim &s, const GLevel &L) {
+    int G = cg_grid(s);
+    return L.g.nblocks < G ? L.g.nblocks : G;
+}
+static int gmg_row_grid(const Sim &s, const GLevel &L) {
+    int G = cdiv(L.nrows, 8), cap = s.num_sms * 8;   // one warp per row, 8 warps per CTA
+    return G < 1 ? 1 : (G > cap ? cap : G);
+}
+
+// Galerkin operators for this solve: unknown flags, row lists, transfer normalisers, A_c = P^T A P / 8
+static void gmg_build(Sim &s, GMG &M) {
+    M.pre = s.mg_sweeps < 1 ? 1 : s.mg_sweeps;
+    M.coarse_sweeps = s.mg_coarse_sweeps;
+    M.omega = s.mg_omega;
+    int want = s.mg_levels < M.nalloc ? (s.mg_levels < 1 ? 1 : s.mg_levels) : M.nalloc;
+    M.nlevels = 1;
+    for (int l = 0; l < want; l++) {
+        GLevel &L = M.lv[l];
+        size_t T = (size_t)L.g.total;
+        // vectors are read with a halo: zero outside the unknowns of THIS solve
+        CUDA_CHECK(cudaMemsetAsync(L.x[0], 0, 3 * T * sizeof(float), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(L.x[1], 0, 3 * T * sizeof(float), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(L.r, 0, 3 * T * sizeof(float), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(L.pn, 0, 3 * T * sizeof(float), s.stream));
+        if (l == 0) continue;
+        GLevel &F = M.lv[l - 1];
+        CUDA_CHECK(cudaMemsetAsync(L.b, 0, 3 * T * sizeof(float), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(L.rowmap, 0xFF, 3 * T * sizeof(int), s.stream));
+        long long n = (long long)(L.g.ni + 1) * (L.g.nj + 1) * (L.g.nk + 1);
+        FLIP_LAUNCH(k_gmg_flags, cdiv(n, 256), 256, s.stream, L.g, F.g, (const float *)F.diag, L.diag);
+        DiagViscosity d{L.diag, L.g.total};
+        build_block_list_on<3>(s, L.g, d, L.blk_flag, L.blk_list, L.blk_count);
+        int G = gmg_grid(s, L);
+        FLIP_LAUNCH_SYNC(k_gmg_row_counts, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
+                         (const float *)L.diag, L.blk_flag);
+        FLIP_LAUNCH_SYNC(k_scan_small, 1, 1024, s.stream, L.blk_flag, (const int *)L.blk_count, L.nrows_dev);
+        FLIP_LAUNCH_SYNC(k_gmg_row_fill, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
+                         (const float *)L.diag, (const int *)L.blk_flag, L.rows, L.rowmap);
+        s.kernel_launches += 4;
+        CUDA_CHECK(cudaMemcpyAsync(M.count_host, L.nrows_dev, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        L.nrows = M.count_host[0];
+        if (L.nrows == 0) break;
+        if ((size_t)L.nrows > L.cap) {
+            if (L.S) { CUDA_CHECK(cudaFree(L.S)); CUDA_CHECK(cudaFree(L.wj)); }
+            L.cap = (size_t)L.nrows + (size_t)L.nrows / 4 + 1024;
+            CUDA_CHECK(cudaMalloc((void **)&L.S, L.cap * GMG_STRIDE * sizeof(float)));
+            CUDA_CHECK(cudaMemsetAsync(L.S, 0, L.cap * GMG_STRIDE * sizeof(float), s.stream));   // padding slots stay 0
+            CUDA_CHECK(cudaMalloc((void **)&L.wj, L.cap * sizeof(float)));
+        }
+        // transfer normaliser of the fine level, then the Galerkin product
+        FLIP_LAUNCH(k_gmg_pnorm, gmg_grid(s, F), CG_THREADS, s.stream, F.g, (const int *)F.blk_list, (const int *)F.blk_count,
+                    (const float *)F.diag, L.g, (const float *)L.diag, F.pn);
+        int GB = 3 * cdiv(L.nrows, GMG_BUILD_THREADS);
+        if (l == 1) {
+            auto kb = &k_gmg_build<true>;
+            FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+                        (const float *)F.diag, (const float *)F.pn, (const float *)s.vcoef, (const int *)nullptr,
+                        (const float *)nullptr, 0);
+        } else {
+            auto kb = &k_gmg_build<false>;
+            FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+                        (const float *)F.diag, (const float *)F.pn, (const float *)nullptr, (const int *)F.rowmap,
+                        (const float *)F.S, F.nrows);
+        }
+        FLIP_LAUNCH_SYNC(k_gmg_diag, cdiv(L.nrows, 8), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const float *)L.S, L.diag, L.wj, M.omega);
+        s.kernel_launches += 3;
+        M.nlevels = l + 1;
+    }
+    KERNEL_CHECK();
+}
+
+// z = Vcycle(r): r is the CG residual (fp64) on level 0.  All grid sizes depend only on what the host
+// knows after gmg_build (row counts), every other argument is a pointer into the hierarchy, so the whole
+// launch sequence can be captured into a CUDA graph once per solve.
+static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const CGState *st) {
+    const float w = M.omega;
+    int cur[GMG_MAX_LEVELS];
+    auto l0_first = &k_gmg0_sweep<0>; auto l0_smooth = &k_gmg0_sweep<1>; auto l0_resid = &k_gmg0_sweep<2>; auto l0_last = &k_gmg0_sweep<3>;
+    auto sweep1 = &k_gmg_sweep<1>; auto sweep2 = &k_gmg_sweep<2>;
+    const int last = M.nlevels - 1;
+    GLevel &L0 = M.lv[0];
+    G0Params P0;
+    P0.g = L0.g; P0.cell_list = s.cell_list; P0.cell_count = s.cell_count; P0.coef = s.vcoef; P0.diag = L0.diag; P0.pn = L0.pn;
+    const int G0 = s.num_sms * 8;
+    const float *nof = nullptr;
+    // level 0, downstroke
+    FLIP_LAUNCH(l0_first, G0, 256, s.stream, P0, r_in, nof, L0.x[0], (double *)nullptr, w, st);
+    cur[0] = 0;
+    if (last == 0) {
+        for (int k = 1; k < 2 * M.pre - 1; k++) {
+            FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+            cur[0] ^= 1;
+        }
+        FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
+        s.kernel_launches += 2 * M.pre;
+        return;
+    }
+    for (int k = 1; k < M.pre; k++) {
+        FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+        cur[0] ^= 1;
+    }
+    FLIP_LAUNCH(l0_resid, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.r, (double *)nullptr, w, st);
+    s.kernel_launches += M.pre + 1;
+    // explicit levels, downstroke
+    for (int l = 1; l <= last; l++) {
+        GLevel &L = M.lv[l];
+        GLevelDev D = gmg_dev(L);
+        int GR = gmg_row_grid(s, L), GT = cdiv(L.nrows, 256);
+        FLIP_LAUNCH(k_gmg_restrict_first, GT, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
+        cur[l] = 0;
+        int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre;
+        for (int k = 1; k < sweeps; k++) {
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            cur[l] ^= 1;
+        }
+        if (l < last) FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
+        s.kernel_launches += sweeps + (l < last ? 1 : 0);
+    }
+    // upstroke
+    for (int l = last - 1; l >= 1; l--) {
+        GLevel &L = M.lv[l];
+        GLevelDev D = gmg_dev(L);
+        int GR = gmg_row_grid(s, L), GT = cdiv(L.nrows, 256);
+        FLIP_LAUNCH(k_gmg_prolong, GT, 256, s.stream, D, (const float *)L.pn, M.lv[l + 1].g, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], st);
+        for (int k = 0; k < M.pre; k++) {
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            cur[l] ^= 1;
+        }
+        s.kernel_launches += 1 + M.pre;
+    }
+    FLIP_LAUNCH(k_gmg0_prolong, G0, 256, s.stream, P0, M.lv[1].g, (const float *)M.lv[1].x[cur[1]], L0.x[cur[0]], st);
+    for (int k = 0; k < M.pre - 1; k++) {
+        FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+        cur[0] ^= 1;
+    }
+    FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
+    s.kernel_launches += 1 + M.pre;
+}
+
+// Multigrid-preconditioned CG: cg.h's run_cg_mg with the iteration chunk (stencil apply, update, V-cycle, dot,
+// direction: ~70 launches per iteration) replayed from a CUDA graph that is re-captured for every solve, because
+// row counts and (after a re-allocation) pointers of the hierarchy change from solve to solve.
+template <class ApplyFn>
+static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double tol_rel, int maxit, ApplyFn apply) {
+    int G = cg_grid(s);
+    auto kinit = &k_cg_init_mg<3, DiagViscosity>;
+    auto kstart = &k_cg_start_mg<3>;
+    auto kdot = &k_cg_dot<3, DiagViscosity>;
+    auto kupdate = &k_cg_update<3, DiagViscosity, true>;
+    auto kdir = &k_cg_direction<3, DiagViscosity, true>;
+    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    gmg_vcycle(s, M, (const double *)P.r, P.z, nullptr);
+    FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, -1);
+    FLIP_LAUNCH(kstart, G, CG_THREADS, s.stream, P);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, 0.0, tol_rel, maxit, 0);
+    s.kernel_launches += 4;
+    KERNEL_CHECK();
+    int chunk = s.mg_chunk < 2 ? 2 : (s.mg_chunk & ~1);
+    long long per_chunk = 0;
+    auto launch_chunk = [&]() {
+        long long before = s.kernel_launches;
+        for (int it = 0; it < chunk; it++) {
+            int parity = it & 1;
+            apply(parity);
+            FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
+            gmg_vcycle(s, M, (const double *)P.r, P.z, (const CGState *)(P.st + parity));
+            FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, parity);
+            FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
+            s.kernel_launches += 4;
+        }
+        per_chunk = s.kernel_launches - before;
+    };
+#ifndef FLIP_CPU_EMU
+    cudaGraphExec_t exec = nullptr;
+    if (s.use_graphs) {
+        cudaGraph_t graph = nullptr;
+        long long keep = s.kernel_launches;
+        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        launch_chunk();
+        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        s.kernel_launches = keep;   // captured, not launched
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+    }
+#endif
+    CGState h;
+    int launched = 0;
+    while (true) {
+        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        h = *s.cgst_host;
+        if (s.verbose > 1) printf("\t\tmg-pcg iteration %d max|r| %.3e (tol %.3e)\n", h.iter, h.resid, h.tol), fflush(stdout);
+        if (h.done || launched >= maxit + chunk) break;
+#ifndef FLIP_CPU_EMU
+        if (exec) { CUDA_CHECK(cudaGraphLaunch(exec, s.stream)); s.kernel_launches += per_chunk; }
+        else
+#endif
+            launch_chunk();
+        KERNEL_CHECK();
+        launched += chunk;
+    }
+#ifndef FLIP_CPU_EMU
+    if (exec) cudaGraphExecDestroy(exec);
+#endif
+    return h;
+}
+
 // _applySolutionToVelocityField: the whole field is cleared, unknowns get (float)soln
 __global__ void __launch_bounds__(256) k_visc_store(Grid g, const float *__restrict__ vdiag, const double *__restrict__ x, float *__restrict__ vel) {
     int i, j, k;
@@ -480,13 +752,20 @@ void stage_apply_viscosity(Sim &s, float dt) {
     CGParams P;
     P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
     P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
-    P.part = s.part; P.st = s.cgst; P.strict = 0;
+    P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
     int G = cg_grid(s);
     const float *vcoef = s.vcoef, *vdiag = s.vdiag;
     cudaStream_t st = s.stream;
     int maxit = s.visc_maxit * s.visc_maxit_scale;
     CGState h;
-    if (s.visc_precond == 1 && s.nranks == 1) {
+    if (s.visc_precond == 2 && s.nranks == 1) {
+        GMG *M = gmg_get(s);
+        gmg_build(s, *M);
+        P.z = s.cg_z;
+        P.flexible = s.mg_flexible;
+        h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit,
+                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity); });
+    } else if (s.visc_precond == 1 && s.nranks == 1) {
         VMG *M = vmg_get(s);
         vmg_build(s, *M);
         P.z = s.cg_z;
@@ -583,7 +862,7 @@ extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y
         CGParams P;
         P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
         P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_z; P.q = s.cg_w; P.z = nullptr;
-        P.part = s.part; P.st = s.cgst; P.strict = 0;
+        P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
         FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, 0);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(y_host, s.cg_w, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -603,5 +882,22 @@ extern "C" int flip_debug_visc_rhs(void *hsim, double *b_host, float *diag_host,
         CUDA_CHECK(cudaMemcpy(diag_host, s.vdiag, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(vol_host, s.vvol + T, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
     } catch (...) { return -2; }
+    return 0;
+}
+
+// explicit Galerkin level of the last solve (tests / dev tools): rows (m*T + padded id) and S [nrows * GMG_STRIDE]
+extern "C" int flip_debug_gmg_level(void *hsim, int level, int *info /*[10]: ni,nj,nk,ax,ay,az,total,nrows,nlevels,stride*/,
+                                    int *rows_out, float *S_out, float *diag_out) {
+    Sim &s = *(Sim *)hsim;
+    GMG *M = (GMG *)s.gmg;
+    if (!M || level < 1 || level >= M->nlevels) return -1;
+    GLevel &L = M->lv[level];
+    const Grid &g = L.g;
+    info[0] = g.ni; info[1] = g.nj; info[2] = g.nk; info[3] = g.ax; info[4] = g.ay; info[5] = g.az; info[6] = g.total;
+    info[7] = L.nrows; info[8] = M->nlevels; info[9] = GMG_STRIDE;
+    cudaStreamSynchronize(s.stream);
+    if (rows_out && cudaMemcpy(rows_out, L.rows, (size_t)L.nrows * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    if (S_out && cudaMemcpy(S_out, L.S, (size_t)L.nrows * GMG_STRIDE * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    if (diag_out && cudaMemcpy(diag_out, L.diag, 3 * (size_t)g.total * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -4;
     return 0;
 }
