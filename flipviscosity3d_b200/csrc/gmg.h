@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_pnorm(Grid g, const int *__r
 // --- fine-operator entry enumeration ---------------------------------------------------------
 // level 0: the <= 7 entries of row (m, id) whose column component is mp (csrc/viscosity.cu k_visc_apply)
 FLIP_D int gmg_entries_l0(int m, int mp, int id, int sy, int sz, size_t T, const float *__restrict__ coef,
-                          const float *__restrict__ diag, int off[7][3], float val[7]) {
+                          const float *__restrict__ vol, int off[7][3], double val[7]) {
     const float *cc = coef, *cu = coef + T, *cv = coef + 2 * T, *cw = coef + 3 * T;
     float fR, fL, fT, fB, fF, fK;
     if (m == 0) { fR = cc[id]; fL = cc[id - 1]; fT = cw[id + sy]; fB = cw[id]; fF = cv[id + sz]; fK = cv[id]; }
@@ -186,7 +186,7 @@ FLIP_D int gmg_entries_l0(int m, int mp, int id, int sy, int sz, size_t T, const
     int n = 0;
 #define GMG_E(di, dj, dk, v) { off[n][0] = di; off[n][1] = dj; off[n][2] = dk; val[n] = v; n++; }
     if (m == mp) {
-        GMG_E(0, 0, 0, diag[m * T + id]) GMG_E(1, 0, 0, -fR) GMG_E(-1, 0, 0, -fL) GMG_E(0, 1, 0, -fT) GMG_E(0, -1, 0, -fB)
+        GMG_E(0, 0, 0, (double)vol[(1 + m) * T + id] + (double)fR + (double)fL + (double)fT + (double)fB + (double)fF + (double)fK) GMG_E(1, 0, 0, -fR) GMG_E(-1, 0, 0, -fL) GMG_E(0, 1, 0, -fT) GMG_E(0, -1, 0, -fB)
         GMG_E(0, 0, 1, -fF) GMG_E(0, 0, -1, -fK)
     } else if (m == 0 && mp == 1) { GMG_E(0, 1, 0, -fT) GMG_E(-1, 1, 0, fT) GMG_E(0, 0, 0, fB) GMG_E(-1, 0, 0, -fB) }
     else if (m == 0 && mp == 2) { GMG_E(0, 0, 1, -fF) GMG_E(-1, 0, 1, fF) GMG_E(0, 0, 0, fK) GMG_E(-1, 0, 0, -fK) }
@@ -221,7 +221,9 @@ FLIP_D void gmg_scatter(double (*acc)[GMG_BUILD_THREADS], const GWin &W, int mp,
             }
 }
 
-// A_c = P^T A P / 8.  One thread per (coarse row, column component); grid = 3 * ceil(nrows / 128).
+// A_c = P^T A P / 8.  One thread per (coarse row I, column component mp); grid = 3 * ceil(nrows / GMG_BUILD_THREADS).
+// The loop runs over the fine COLUMNS j that can reach a child of I: t_j = sum_i P[i,I] A[i,j] is gathered from
+// row j of the (symmetric) fine operator, then scattered once to the <= 8 coarse parents of j.
 // FINE0: the fine level is level 0 (matrix-free coefficients), else an explicit stencil level.
 template <bool FINE0>
 __global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, int nrows_c,
@@ -229,9 +231,8 @@ __global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid g
                                                                   const float *__restrict__ diag_f, const float *__restrict__ pn_f,
                                                                   const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
                                                                   const float *__restrict__ S_f, int nrows_f) {
-    // fp64 accumulation: the mass term of a coarse row (its row sum, ~1) is what remains of ~5000 products of size
-    // ~1e4 that cancel; in fp32 it came out with O(1) relative error at 256^3, the near-rigid coarse modes lost
-    // their (tiny, positive) energy and the V-cycle stopped being positive definite.
+    // fp64 accumulation: the mass term of a coarse row (its row sum, ~1) is what remains of thousands of products
+    // of size ~1e4 that cancel.
     __shared__ double acc[80][GMG_BUILD_THREADS];
     const int mp = blockIdx.x % 3;
     const int r = (blockIdx.x / 3) * GMG_BUILD_THREADS + threadIdx.x;
@@ -244,55 +245,71 @@ __global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid g
     const GWin W = gmg_window(m, mp);
     for (int q = 0; q < W.size; q++) acc[q][threadIdx.x] = 0.0;
     const int sy = SY(gf), sz = SZ(gf);
-    int li, ci, lj, cj, lk, ck;
-    float wi[4], wj[4], wk[4];
-    vmg_axis(m == 0, I, li, ci, wi);
-    vmg_axis(m == 1, J, lj, cj, wj);
-    vmg_axis(m == 2, K, lk, ck, wk);
-    for (int c2 = 0; c2 < ck; c2++) {
-        int fk = lk + c2;
-        if (fk < 0 || fk > gf.nk) continue;
-        for (int b2 = 0; b2 < cj; b2++) {
-            int fj = lj + b2;
-            if (fj < 0 || fj > gf.nj) continue;
-            for (int a = 0; a < ci; a++) {
-                int fi = li + a;
-                if (fi < 0 || fi > gf.ni) continue;
-                int idf = gidx(gf, fi, fj, fk);
-                if (diag_f[m * Tf + idf] == 0.0f) continue;
-                float pnf = pn_f[m * Tf + idf];
-                if (pnf == 0.0f) continue;
-                double wP = (double)(wi[a] * wj[b2] * wk[c2]) / (double)pnf;
+    // children of I (component m) and their prolongation weights P[i,I]
+    int lo[3], cn[3];
+    float wa[3][4];
+    vmg_axis(m == 0, I, lo[0], cn[0], wa[0]);
+    vmg_axis(m == 1, J, lo[1], cn[1], wa[1]);
+    vmg_axis(m == 2, K, lo[2], cn[2], wa[2]);
+    const int nf[3] = {gf.ni, gf.nj, gf.nk};
+    float wP[64];
+    for (int c2 = 0; c2 < 4; c2++)
+        for (int b2 = 0; b2 < 4; b2++)
+            for (int a = 0; a < 4; a++) {
+                float w = 0.0f;
+                int fi = lo[0] + a, fj = lo[1] + b2, fk = lo[2] + c2;
+                if (a < cn[0] && b2 < cn[1] && c2 < cn[2] && fi >= 0 && fj >= 0 && fk >= 0 && fi <= nf[0] && fj <= nf[1] && fk <= nf[2]) {
+                    size_t o = m * Tf + gidx(gf, fi, fj, fk);
+                    float p = pn_f[o];
+                    if (diag_f[o] != 0.0f && p > 0.0f) w = wa[0][a] * wa[1][b2] * wa[2][c2] / p;
+                }
+                wP[(c2 * 4 + b2) * 4 + a] = w;
+            }
+    // offsets o = i - j of row j (component mp) towards component m
+    const GWin R = gmg_window(mp, m);
+    int olo[3], ohi[3], jlo[3], jhi[3];
+    for (int a = 0; a < 3; a++) {
+        olo[a] = FINE0 ? -1 : R.lo[a];
+        ohi[a] = FINE0 ? 1 : R.lo[a] + R.n[a] - 1;
+        jlo[a] = lo[a] - ohi[a] < 0 ? 0 : lo[a] - ohi[a];
+        jhi[a] = lo[a] + cn[a] - 1 - olo[a] > nf[a] ? nf[a] : lo[a] + cn[a] - 1 - olo[a];
+    }
+    for (int jk = jlo[2]; jk <= jhi[2]; jk++)
+        for (int jj = jlo[1]; jj <= jhi[1]; jj++)
+            for (int ji = jlo[0]; ji <= jhi[0]; ji++) {
+                const int idj = gidx(gf, ji, jj, jk);
+                const size_t oj = mp * Tf + idj;
+                if (diag_f[oj] == 0.0f) continue;             // column is not an unknown: entries dropped
+                const float pnj = pn_f[oj];
+                if (pnj == 0.0f) continue;
+                double t = 0.0;
                 if (FINE0) {
                     int off[7][3];
-                    float val[7];
-                    int ne = gmg_entries_l0(m, mp, idf, sy, sz, Tf, coef_f, diag_f, off, val);
+                    double val[7];
+                    int ne = gmg_entries_l0(mp, m, idj, sy, sz, Tf, coef_f, S_f /* level 0: the volume grids */, off, val);
                     for (int e = 0; e < ne; e++) {
-                        int ji = fi + off[e][0], jj = fj + off[e][1], jk = fk + off[e][2];
-                        size_t oj = mp * Tf + idf + off[e][0] + off[e][1] * sy + off[e][2] * sz;
-                        if (diag_f[oj] == 0.0f) continue;         // column is not an unknown: entry dropped
-                        float pnj = pn_f[oj];
-                        if (pnj == 0.0f) continue;
-                        gmg_scatter(acc, W, mp, wP * (double)val[e] / (double)pnj, ji, jj, jk, I, J, K, gc, diag_c);
+                        int a = ji + off[e][0] - lo[0], b2 = jj + off[e][1] - lo[1], c2 = jk + off[e][2] - lo[2];
+                        if (a < 0 || b2 < 0 || c2 < 0 || a >= cn[0] || b2 >= cn[1] || c2 >= cn[2]) continue;
+                        t += (double)wP[(c2 * 4 + b2) * 4 + a] * val[e];
                     }
                 } else {
-                    int rf = rowmap_f[m * Tf + idf];
-                    const GWin F = gmg_window(m, mp);
-                    int slot = F.base;
-                    for (int dk = F.lo[2]; dk < F.lo[2] + F.n[2]; dk++)
-                        for (int dj = F.lo[1]; dj < F.lo[1] + F.n[1]; dj++)
-                            for (int di = F.lo[0]; di < F.lo[0] + F.n[0]; di++, slot++) {
-                                float v = S_f[(size_t)rf * GMG_STRIDE + slot];
-                                if (v == 0.0f) continue;
-                                size_t oj = mp * Tf + idf + di + dj * sy + dk * sz;
-                                float pnj = pn_f[oj];
-                                if (pnj == 0.0f) continue;
-                                gmg_scatter(acc, W, mp, wP * (double)v / (double)pnj, fi + di, fj + dj, fk + dk, I, J, K, gc, diag_c);
-                            }
+                    const float *__restrict__ Sj = S_f + (size_t)rowmap_f[oj] * GMG_STRIDE + R.base;
+                    // children i = j + o with o inside the window of row j
+                    int a0 = ji + olo[0] - lo[0], a1 = ji + ohi[0] - lo[0];
+                    int b0 = jj + olo[1] - lo[1], b1 = jj + ohi[1] - lo[1];
+                    int c0 = jk + olo[2] - lo[2], c1 = jk + ohi[2] - lo[2];
+                    a0 = a0 < 0 ? 0 : a0; b0 = b0 < 0 ? 0 : b0; c0 = c0 < 0 ? 0 : c0;
+                    a1 = a1 > cn[0] - 1 ? cn[0] - 1 : a1; b1 = b1 > cn[1] - 1 ? cn[1] - 1 : b1; c1 = c1 > cn[2] - 1 ? cn[2] - 1 : c1;
+                    for (int c2 = c0; c2 <= c1; c2++)
+                        for (int b2 = b0; b2 <= b1; b2++) {
+                            const float *__restrict__ Sr = Sj + ((lo[2] + c2 - jk - R.lo[2]) * R.n[1] + (lo[1] + b2 - jj - R.lo[1])) * R.n[0] +
+                                                           (lo[0] - ji - R.lo[0]);
+                            for (int a = a0; a <= a1; a++) t += (double)wP[(c2 * 4 + b2) * 4 + a] * (double)Sr[a];
+                        }
                 }
+                if (t == 0.0) continue;
+                gmg_scatter(acc, W, mp, t / (double)pnj, ji, jj, jk, I, J, K, gc, diag_c);
             }
-        }
-    }
     for (int q = 0; q < W.size; q++) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q][threadIdx.x]);
 }
 
@@ -387,6 +404,7 @@ struct G0Params {
     Grid g;
     const int *cell_list, *cell_count;
     const float *coef, *diag, *pn;
+    const float *vol;     // the solver's 7 volume grids (vvol); faces U,V,W are grids 1,2,3
 };
 
 template <int MODE>
@@ -423,18 +441,18 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
         float aU = 0.0f, aV = 0.0f, aW = 0.0f;
         if (dU != 0.0f) {
             const float fR = c0, fL = c_xm, fT = ew_yp, fB = ew0, fF = ev_zp, fK = ev0;
-            aU = dU * u0 - fR * u_xp - fL * u_xm - fT * u_yp - fB * u_ym - fF * u_zp - fK * u_zm - fT * v_yp + fT * v_xm_yp +
-                 fB * v0 - fB * v_xm - fF * w_zp + fF * w_xm_zp + fK * w0 - fK * w_xm;
+            aU = L.vol[T + id] * u0 + fR * (u0 - u_xp) + fL * (u0 - u_xm) + fT * (u0 - u_yp) + fB * (u0 - u_ym) + fF * (u0 - u_zp) +
+                 fK * (u0 - u_zm) - fT * (v_yp - v_xm_yp) + fB * (v0 - v_xm) - fF * (w_zp - w_xm_zp) + fK * (w0 - w_xm);
         }
         if (dV != 0.0f) {
             const float fR = ew_xp, fL = ew0, fT = c0, fB = c_ym, fF = eu_zp, fK = eu0;
-            aV = dV * v0 - fR * v_xp - fL * v_xm - fT * v_yp - fB * v_ym - fF * v_zp - fK * v_zm - fR * u_xp + fR * u_xp_ym +
-                 fL * u0 - fL * u_ym - fF * w_zp + fF * w_ym_zp + fK * w0 - fK * w_ym;
+            aV = L.vol[2 * T + id] * v0 + fR * (v0 - v_xp) + fL * (v0 - v_xm) + fT * (v0 - v_yp) + fB * (v0 - v_ym) + fF * (v0 - v_zp) +
+                 fK * (v0 - v_zm) - fR * (u_xp - u_xp_ym) + fL * (u0 - u_ym) - fF * (w_zp - w_ym_zp) + fK * (w0 - w_ym);
         }
         if (dW != 0.0f) {
             const float fR = ev_xp, fL = ev0, fT = eu_yp, fB = eu0, fF = c0, fK = c_zm;
-            aW = dW * w0 - fR * w_xp - fL * w_xm - fT * w_yp - fB * w_ym - fF * w_zp - fK * w_zm - fR * u_xp + fR * u_xp_zm +
-                 fL * u0 - fL * u_zm - fT * v_yp + fT * v_yp_zm + fB * v0 - fB * v_zm;
+            aW = L.vol[3 * T + id] * w0 + fR * (w0 - w_xp) + fL * (w0 - w_xm) + fT * (w0 - w_yp) + fB * (w0 - w_ym) + fF * (w0 - w_zp) +
+                 fK * (w0 - w_zm) - fR * (u_xp - u_xp_zm) + fL * (u0 - u_zm) - fT * (v_yp - v_yp_zm) + fB * (v0 - v_zm);
         }
         if (MODE == 2) {
             const float pU = L.pn[id], pV = L.pn[T + id], pW = L.pn[2 * T + id];

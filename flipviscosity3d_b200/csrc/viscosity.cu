@@ -237,8 +237,17 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
 }
 
 // phase A: q = A s for the three face families of each cell index
+//
+// Every row is evaluated in DIFFERENCE form,  q = vol * s0 + sum_k f_k (s0 - s_k) + cross differences,  which is
+// the same row as  d * s0 - sum_k f_k s_k - ...  with d = vol + sum_k f_k  (src/viscositysolver.cpp:429) in exact
+// arithmetic.  The reference forms d in fp32; at 256^3 the six factors add up to ~2e4, ulp(2e4) = 2e-3, so the
+// face-volume ("mass") term vol <= 1 of every row is rounded to within +-1e-3 and comes out NEGATIVE on thousands
+// of thin free-surface faces: the assembled matrix is no longer positive definite, CG wanders (measured on a scipy
+// copy of the system: 64 multigrid-PCG iterations with the exact diagonal, 307 with the fp32 one, Jacobi-PCG 3484
+// vs 5686) and the reference's own MICCG(0) stops at its 700-iteration cap.  The difference form keeps the mass
+// term exact; the two operators differ by that rounding noise only (<= 1e-7 relative per diagonal entry).
 __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const float *__restrict__ vcoef,
-                                                           const float *__restrict__ vdiag, int parity) {
+                                                           const float *__restrict__ vdiag, const float *__restrict__ vvol, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     if (P.st[parity].done) return;
     const Grid &g = P.g;
@@ -269,22 +278,25 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
         const double ew0 = cw[id], ew_xp = cw[id + 1], ew_yp = cw[id + sy];
         if (dU != 0.0f) {
             const double fR = c0, fL = c_xm, fT = ew_yp, fB = ew0, fF = ev_zp, fK = ev0;
-            double q = (double)dU * u0 - fR * u_xp - fL * u_xm - fT * u_yp - fB * u_ym - fF * u_zp - fK * u_zm - fT * v_yp +
-                       fT * v_xm_yp + fB * v0 - fB * v_xm - fF * w_zp + fF * w_xm_zp + fK * w0 - fK * w_xm;
+            double q = (double)vvol[T + id] * u0 + fR * (u0 - u_xp) + fL * (u0 - u_xm) + fT * (u0 - u_yp) + fB * (u0 - u_ym) +
+                       fF * (u0 - u_zp) + fK * (u0 - u_zm) - fT * (v_yp - v_xm_yp) + fB * (v0 - v_xm) - fF * (w_zp - w_xm_zp) +
+                       fK * (w0 - w_xm);
             P.q[id] = q;
             sq += u0 * q;
         }
         if (dV != 0.0f) {
             const double fR = ew_xp, fL = ew0, fT = c0, fB = c_ym, fF = eu_zp, fK = eu0;
-            double q = (double)dV * v0 - fR * v_xp - fL * v_xm - fT * v_yp - fB * v_ym - fF * v_zp - fK * v_zm - fR * u_xp +
-                       fR * u_xp_ym + fL * u0 - fL * u_ym - fF * w_zp + fF * w_ym_zp + fK * w0 - fK * w_ym;
+            double q = (double)vvol[2 * T + id] * v0 + fR * (v0 - v_xp) + fL * (v0 - v_xm) + fT * (v0 - v_yp) + fB * (v0 - v_ym) +
+                       fF * (v0 - v_zp) + fK * (v0 - v_zm) - fR * (u_xp - u_xp_ym) + fL * (u0 - u_ym) - fF * (w_zp - w_ym_zp) +
+                       fK * (w0 - w_ym);
             P.q[T + id] = q;
             sq += v0 * q;
         }
         if (dW != 0.0f) {
             const double fR = ev_xp, fL = ev0, fT = eu_yp, fB = eu0, fF = c0, fK = c_zm;
-            double q = (double)dW * w0 - fR * w_xp - fL * w_xm - fT * w_yp - fB * w_ym - fF * w_zp - fK * w_zm - fR * u_xp +
-                       fR * u_xp_zm + fL * u0 - fL * u_zm - fT * v_yp + fT * v_yp_zm + fB * v0 - fB * v_zm;
+            double q = (double)vvol[3 * T + id] * w0 + fR * (w0 - w_xp) + fL * (w0 - w_xm) + fT * (w0 - w_yp) + fB * (w0 - w_ym) +
+                       fF * (w0 - w_zp) + fK * (w0 - w_zm) - fR * (u_xp - u_xp_zm) + fL * (u0 - u_zm) - fT * (v_yp - v_yp_zm) +
+                       fB * (v0 - v_zm);
             P.q[2 * T + id] = q;
             sq += w0 * q;
         }
@@ -567,7 +579,7 @@ static void gmg_build(Sim &s, GMG &M) {
             auto kb = &k_gmg_build<true>;
             FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)s.vcoef, (const int *)nullptr,
-                        (const float *)nullptr, 0);
+                        (const float *)s.vvol, 0);
         } else {
             auto kb = &k_gmg_build<false>;
             FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
@@ -592,7 +604,7 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
     const int last = M.nlevels - 1;
     GLevel &L0 = M.lv[0];
     G0Params P0;
-    P0.g = L0.g; P0.cell_list = s.cell_list; P0.cell_count = s.cell_count; P0.coef = s.vcoef; P0.diag = L0.diag; P0.pn = L0.pn;
+    P0.g = L0.g; P0.cell_list = s.cell_list; P0.cell_count = s.cell_count; P0.coef = s.vcoef; P0.diag = L0.diag; P0.pn = L0.pn; P0.vol = s.vvol;
     const int G0 = s.num_sms * 8;
     const float *nof = nullptr;
     // level 0, downstroke
@@ -754,7 +766,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
     P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
     int G = cg_grid(s);
-    const float *vcoef = s.vcoef, *vdiag = s.vdiag;
+    const float *vcoef = s.vcoef, *vdiag = s.vdiag, *vvol = s.vvol;
     cudaStream_t st = s.stream;
     int maxit = s.visc_maxit * s.visc_maxit_scale;
     CGState h;
@@ -764,25 +776,25 @@ void stage_apply_viscosity(Sim &s, float dt) {
         P.z = s.cg_z;
         P.flexible = s.mg_flexible;
         h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit,
-                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity); });
+                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); });
     } else if (s.visc_precond == 1 && s.nranks == 1) {
         VMG *M = vmg_get(s);
         vmg_build(s, *M);
         P.z = s.cg_z;
         h = run_cg_mg<3>(s, P, diag, 0.0, s.visc_tol, maxit,
-                         [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity); },
+                         [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); },
                          [&](const CGState *cst) { vmg_vcycle(s, *M, (const double *)P.r, P.z, cst); });
     } else if (s.cg_variant_viscosity == 1) {
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
         h = run_cg2<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Pu, vcoef, vdiag, parity);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Pu, vcoef, vdiag, vvol, parity);
         }, 1);
     } else {
         h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
             dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, parity);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity);
         }, 1, s.visc_warm_start ? (const float *)s.vel : nullptr);
     }
     dist_allgather_slabs(s, s.cg_x, 3);
@@ -863,7 +875,7 @@ extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y
         P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
         P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_z; P.q = s.cg_w; P.z = nullptr;
         P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
-        FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, 0);
+        FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(y_host, s.cg_w, n * sizeof(double), cudaMemcpyDeviceToHost));
     } catch (...) { return -2; }
