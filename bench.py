@@ -11,8 +11,11 @@ substep of FluidSimulation::advance() (/root/reference/src/fluidsimulation.cpp:1
   value     substeps/s with all state resident in HBM (device time of K substeps)
   e2e       the same through the C ABI with HOST particle buffers: every step uploads the particles
             (flip_set_particles), runs the substep and reads them back (flip_get_particles)
-  roofline  dominant kernel group = the viscosity CG iteration; achieved = SURVEY §8(d) bytes
-            (13*8+16 = 120 B per unknown per iteration) x unknowns x iterations / solve time
+  roofline  dominant kernel = the Jacobi sweep on the first explicit level of the Galerkin multigrid that
+            preconditions the viscosity CG (k_gmg_sweep<1>, ~30 % of the substep): algorithmic bytes =
+            rows x (235 stencil coefficients + row index + weight + b + x in + x out) x 4 B, divided by its
+            average launch duration measured with CUDA events on the library's stream (flip_time_kernel)
+            right after the timed region, on the hierarchy of the last timed substep
   cpu_baseline  the reference's own C++ path (oracle/_ref, 1 thread: it has no threading) on a
             bounded sample: one substep of the same scene at 128^3
   --impl reference   the reference's CPU implementation on the 256^3 workload itself, bounded to
@@ -95,10 +98,10 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def ncu_traffic():
-    """dram bytes per CG iteration from the committed ncu capture (profiles/), if present."""
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), if present."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["viscosity_iteration_dram_bytes"]
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["kernels"][kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -150,8 +153,9 @@ def run_reference(args):
 def workload_config(args, particles):
     return {"workload": "bunny_in_sphere_%d^3_8ppc_viscosity%g (BASELINE.json configs[3])" % (args.size, args.viscosity),
             "grid": [args.size] * 3, "particles": int(particles), "viscosity": args.viscosity, "frame_dt": FRAME_DT,
-            "step": "one substep of FluidSimulation::advance", "parallelism": "k-slab CG x%d (particle/grid stages replicated; per-iteration exchanges %s)" % (args.gpus, "NCCL" if getattr(args, "no_p2p", False) else "peer memory over NVLink"),
-            "l2": "working set (fields + CG vectors of the active blocks) exceeds the 126 MB L2; no flush between steps"}
+            "step": "one substep of FluidSimulation::advance", "parallelism": "x%d: pressure CG k-slab decomposed (exchanges over %s); multigrid viscosity solve and particle/grid stages replicated" % (args.gpus, "NCCL" if getattr(args, "no_p2p", False) else "peer memory over NVLink"),
+            "viscosity_solver": "PCG, Galerkin multigrid V(2,2) preconditioner (viscosity_precond=%d)" % getattr(args, "precond", 2),
+            "l2": "working set (fields, CG vectors, 280 MB of level-1 multigrid coefficients) exceeds the 126 MB L2; no flush between steps"}
 
 
 def run_b200(args):
@@ -178,6 +182,7 @@ def run_b200(args):
     sim.set_solid_sdf(phi)
     sim.set_particles(p)
     sim.set_viscosity(visc)
+    sim.set_param("viscosity_precond", args.precond)
     if world > 1:
         # NCCL communicator of the library: rank 0 makes the unique id, torch.distributed ships it
         box = [sim.dist_unique_id() if rank == 0 else None]
@@ -239,10 +244,24 @@ def run_b200(args):
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     peak, peak_kind = measured_peak()
-    vis_dom = iters["v_ms"] >= iters["p_ms"]
-    alg = (ALG_BYTES_VISC * iters["v_unk"]) if vis_dom else (ALG_BYTES_PRES * iters["p_unk"])
-    solve_ms = iters["v_ms"] if vis_dom else iters["p_ms"]
-    achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    # dominant kernel, timed live with CUDA events on the library's stream (hierarchy of the last substep)
+    roof = None
+    try:
+        k_ms, k_bytes = sim.time_kernel("gmg_sweep_l1", 40)
+        a_ms, a_bytes = sim.time_kernel("visc_apply", 40)
+        roof = {"bound": "hbm", "kernel": "k_gmg_sweep<1> on multigrid level 1 (Jacobi sweep over explicit 235-slot Galerkin rows, one warp per row)",
+                "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_kind": peak_kind,
+                "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes, "traffic": ncu_traffic("gmg_sweep_l1"),
+                "other_kernels": {"k_visc_apply": {"ms_per_launch": a_ms, "algorithmic_bytes_per_launch": a_bytes,
+                                                    "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "traffic": ncu_traffic("visc_apply")}}}
+        roof["frac"] = roof["achieved"] / peak
+    except Exception as e:   # diagonal preconditioner selected: fall back to the CG-iteration figure
+        vis_dom = iters["v_ms"] >= iters["p_ms"]
+        alg = (ALG_BYTES_VISC * iters["v_unk"]) if vis_dom else (ALG_BYTES_PRES * iters["p_unk"])
+        solve_ms = iters["v_ms"] if vis_dom else iters["p_ms"]
+        achieved = alg / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "CG iteration (stencil apply + update + direction)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None, "note": str(e)}
 
     if rank == 0:
         cpu = None
@@ -263,11 +282,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(host.nbytes), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "viscosity CG iteration (k_visc_apply + k_cg_update + k_cg_direction)"
-                         if vis_dom else "pressure CG iteration (k_pressure_apply + k_cg_update + k_cg_direction)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_kind": peak_kind, "traffic": ncu_traffic(),
-                         "algorithmic_bytes_per_unknown_iteration": ALG_BYTES_VISC if vis_dom else ALG_BYTES_PRES},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "stage_ms": (stage / args.steps).tolist(),
@@ -292,6 +307,7 @@ def main():
     ap.add_argument("--viscosity", type=float, default=5.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: keep NCCL for the per-iteration exchanges")
+    ap.add_argument("--precond", type=int, default=2, help="viscosity preconditioner: 2 Galerkin multigrid (default), 0 diagonal")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -580,6 +580,18 @@ int flip_get_stats(flip_sim *h, flip_stats *out) {
     return FLIP_OK;
 }
 
+int flip_time_kernel(flip_sim *h, const char *name, int reps, float *ms_per_launch, uint64_t *algorithmic_bytes) {
+    if (!h || !name || !ms_per_launch || !algorithmic_bytes) return FLIP_EINVAL;
+    Sim &s = h->s;
+    try {
+        unsigned long long b = 0;
+        int rc = viscosity_time_kernel(s, name, reps, ms_per_launch, &b);
+        *algorithmic_bytes = b;
+        if (rc != 0) return fail_inval(s, rc == -2 ? "flip_time_kernel: unknown kernel name" : "flip_time_kernel: no viscosity solve to time yet");
+    } catch (const std::exception &e) { s.last_error = e.what(); return FLIP_ECUDA; }
+    return FLIP_OK;
+}
+
 int flip_dist_unique_id(void *out128) {
     if (!out128) return FLIP_EINVAL;
     try { dist_get_unique_id(out128); } catch (const std::exception &e) { g_create_error = e.what(); return FLIP_ENCCL; }

@@ -27,7 +27,6 @@
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
-#define GMG_BUILD_THREADS 64      // x 80 fp64 accumulators = 40 KB of shared memory
 
 struct GWin { int lo[3], n[3], base, size; };
 
@@ -59,6 +58,7 @@ struct GLevel {
     size_t cap = 0;       // rows S is allocated for
     float *S = 0;         // [nrows * GMG_STRIDE]
     float *wj = 0;        // [nrows] smoothing weight per row
+    int *offs = 0;        // [3 * GMG_STRIDE] slot -> element offset table (set once: it only depends on the grid)
     bool owns = false;
 };
 
@@ -77,6 +77,7 @@ struct GLevelDev {
     const int *nrows;
     const float *S;
     const float *wj;     // [nrows] smoothing weights
+    const int *offs;     // [3 * GMG_STRIDE] element offset of every slot, per row component (0 for padding)
 };
 
 FLIP_D void gmg_unflatten(const Grid &g, int id, int &i, int &j, int &k) {
@@ -198,91 +199,87 @@ FLIP_D int gmg_entries_l0(int m, int mp, int id, int sy, int sz, size_t T, const
     return n;
 }
 
-// scatter one fine entry (row weight wP, value a, column (mp; ji,jj,jk)) to the coarse parents of the column
-FLIP_D void gmg_scatter(double (*acc)[GMG_BUILD_THREADS], const GWin &W, int mp, double wa, int ji, int jj, int jk, int I, int J, int K,
-                        const Grid &gc, const float *__restrict__ diag_c) {
-    int pi[2], pj[2], pk[2];
-    float wi[2], wj[2], wk[2];
-    vmg_parents(mp == 0, ji, pi[0], pi[1], wi[0], wi[1]);
-    vmg_parents(mp == 1, jj, pj[0], pj[1], wj[0], wj[1]);
-    vmg_parents(mp == 2, jk, pk[0], pk[1], wk[0], wk[1]);
-    const float *d = diag_c + (size_t)mp * gc.total;
-    for (int c2 = 0; c2 < 2; c2++)
-        for (int b2 = 0; b2 < 2; b2++)
-            for (int a = 0; a < 2; a++) {
-                float w = wi[a] * wj[b2] * wk[c2];
-                if (w == 0.0f) continue;
-                int PI = pi[a], PJ = pj[b2], PK = pk[c2];
-                if (PI < 0 || PJ < 0 || PK < 0 || PI > gc.ni || PJ > gc.nj || PK > gc.nk) continue;
-                if (d[gidx(gc, PI, PJ, PK)] == 0.0f) continue;
-                int oi = PI - I - W.lo[0], oj = PJ - J - W.lo[1], ok = PK - K - W.lo[2];
-                if (oi < 0 || oj < 0 || ok < 0 || oi >= W.n[0] || oj >= W.n[1] || ok >= W.n[2]) continue;  // cannot happen
-                acc[(ok * W.n[1] + oj) * W.n[0] + oi][threadIdx.x] += wa * (double)w;
-            }
-}
-
-// A_c = P^T A P / 8.  One thread per (coarse row I, column component mp); grid = 3 * ceil(nrows / GMG_BUILD_THREADS).
-// The loop runs over the fine COLUMNS j that can reach a child of I: t_j = sum_i P[i,I] A[i,j] is gathered from
-// row j of the (symmetric) fine operator, then scattered once to the <= 8 coarse parents of j.
-// FINE0: the fine level is level 0 (matrix-free coefficients), else an explicit stencil level.
+// A_c = P^T A P / 8.  One WARP per (coarse row I, column component mp); grid = ceil(3 * nrows / 8) CTAs of 8 warps.
+// The warp walks the fine COLUMNS j that can reach a child of I, 32 at a time (one per lane):
+//   t_j = sum_i P[i,I] A[i,j]   is gathered by the lane from row j of the (symmetric) fine operator, so the global
+//                               loads of 32 columns are in flight together;
+//   the <= 8 contributions t_j P[j,J] of every lane are then added to the warp's 80 fp64 accumulators in shared
+//   memory in LANE ORDER (staged in shared memory; contribution c of lane l is applied by lane c in step l: the 8
+//   parents of a column are distinct slots), so the sums are formed in a fixed order: no atomics, bit-reproducible.
+// fp64 accumulation: the mass term of a coarse row (its row sum, ~1) is what remains of thousands of products of
+// size ~1e4 that cancel.  FINE0: the fine level is level 0 (matrix-free coefficients), else an explicit level.
+#define GMG_BUILD_WARPS 8
 template <bool FINE0>
-__global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, int nrows_c,
-                                                                  const float *__restrict__ diag_c, float *__restrict__ S_c,
-                                                                  const float *__restrict__ diag_f, const float *__restrict__ pn_f,
-                                                                  const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
-                                                                  const float *__restrict__ S_f, int nrows_f) {
-    // fp64 accumulation: the mass term of a coarse row (its row sum, ~1) is what remains of thousands of products
-    // of size ~1e4 that cancel.
-    __shared__ double acc[80][GMG_BUILD_THREADS];
-    const int mp = blockIdx.x % 3;
-    const int r = (blockIdx.x / 3) * GMG_BUILD_THREADS + threadIdx.x;
-    if (r >= nrows_c) return;
+__global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, int nrows_c,
+                                                                     const float *__restrict__ diag_c, float *__restrict__ S_c,
+                                                                     const float *__restrict__ diag_f, const float *__restrict__ pn_f,
+                                                                     const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
+                                                                     const float *__restrict__ S_f, int nrows_f) {
+    __shared__ double acc_s[GMG_BUILD_WARPS][80];
+    __shared__ float wP_s[GMG_BUILD_WARPS][64];
+    __shared__ int sslot_s[GMG_BUILD_WARPS][256];
+    __shared__ double sval_s[GMG_BUILD_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int task = blockIdx.x * GMG_BUILD_WARPS + wid;        // (row, mp), mp fastest
+    if (task >= 3 * nrows_c) return;                            // whole warp leaves together; no block-wide barrier below
+    const int r = task / 3, mp = task - 3 * r;
+    double *acc = acc_s[wid];
+    float *wP = wP_s[wid];
+    int *sslot = sslot_s[wid];
+    double *sval = sval_s[wid];
     const size_t Tc = (size_t)gc.total, Tf = (size_t)gf.total;
     const int enc = rows_c[r];
     const int m = enc / (int)Tc, idc = enc - m * (int)Tc;
     int I, J, K;
     gmg_unflatten(gc, idc, I, J, K);
     const GWin W = gmg_window(m, mp);
-    for (int q = 0; q < W.size; q++) acc[q][threadIdx.x] = 0.0;
+    for (int q = lane; q < 80; q += 32) acc[q] = 0.0;
     const int sy = SY(gf), sz = SZ(gf);
-    // children of I (component m) and their prolongation weights P[i,I]
-    int lo[3], cn[3];
-    float wa[3][4];
-    vmg_axis(m == 0, I, lo[0], cn[0], wa[0]);
-    vmg_axis(m == 1, J, lo[1], cn[1], wa[1]);
-    vmg_axis(m == 2, K, lo[2], cn[2], wa[2]);
+    // children of I (component m) and their prolongation weights P[i,I]: a 4 x 4 x 4 box from (2I-1, 2J-1, 2K-1)
+    const int lo[3] = {2 * I - 1, 2 * J - 1, 2 * K - 1};
+    const int cn[3] = {m == 0 ? 3 : 4, m == 1 ? 3 : 4, m == 2 ? 3 : 4};
     const int nf[3] = {gf.ni, gf.nj, gf.nk};
-    float wP[64];
-    for (int c2 = 0; c2 < 4; c2++)
-        for (int b2 = 0; b2 < 4; b2++)
-            for (int a = 0; a < 4; a++) {
-                float w = 0.0f;
-                int fi = lo[0] + a, fj = lo[1] + b2, fk = lo[2] + c2;
-                if (a < cn[0] && b2 < cn[1] && c2 < cn[2] && fi >= 0 && fj >= 0 && fk >= 0 && fi <= nf[0] && fj <= nf[1] && fk <= nf[2]) {
-                    size_t o = m * Tf + gidx(gf, fi, fj, fk);
-                    float p = pn_f[o];
-                    if (diag_f[o] != 0.0f && p > 0.0f) w = wa[0][a] * wa[1][b2] * wa[2][c2] / p;
-                }
-                wP[(c2 * 4 + b2) * 4 + a] = w;
-            }
-    // offsets o = i - j of row j (component mp) towards component m
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        int q = lane + 32 * t;
+        int a = q & 3, b2 = (q >> 2) & 3, c2 = q >> 4;
+        int fi = lo[0] + a, fj = lo[1] + b2, fk = lo[2] + c2;
+        float wi = m == 0 ? (a == 1 ? 1.0f : (a < 3 ? 0.5f : 0.0f)) : ((a == 1 || a == 2) ? 0.75f : 0.25f);
+        float wj = m == 1 ? (b2 == 1 ? 1.0f : (b2 < 3 ? 0.5f : 0.0f)) : ((b2 == 1 || b2 == 2) ? 0.75f : 0.25f);
+        float wk = m == 2 ? (c2 == 1 ? 1.0f : (c2 < 3 ? 0.5f : 0.0f)) : ((c2 == 1 || c2 == 2) ? 0.75f : 0.25f);
+        float w = wi * wj * wk;
+        if (w != 0.0f && fi >= 0 && fj >= 0 && fk >= 0 && fi <= nf[0] && fj <= nf[1] && fk <= nf[2]) {
+            size_t o = m * Tf + gidx(gf, fi, fj, fk);
+            float p = pn_f[o];
+            w = (diag_f[o] != 0.0f && p > 0.0f) ? w / p : 0.0f;
+        } else w = 0.0f;
+        wP[q] = w;
+    }
+    __syncwarp();
+    // offsets o = i - j of row j (component mp) towards component m, and the box of candidate columns
     const GWin R = gmg_window(mp, m);
-    int olo[3], ohi[3], jlo[3], jhi[3];
+    int olo[3], ohi[3], jlo[3], jn[3];
     for (int a = 0; a < 3; a++) {
         olo[a] = FINE0 ? -1 : R.lo[a];
         ohi[a] = FINE0 ? 1 : R.lo[a] + R.n[a] - 1;
         jlo[a] = lo[a] - ohi[a] < 0 ? 0 : lo[a] - ohi[a];
-        jhi[a] = lo[a] + cn[a] - 1 - olo[a] > nf[a] ? nf[a] : lo[a] + cn[a] - 1 - olo[a];
+        int jhi = lo[a] + cn[a] - 1 - olo[a] > nf[a] ? nf[a] : lo[a] + cn[a] - 1 - olo[a];
+        jn[a] = jhi - jlo[a] + 1;
+        if (jn[a] < 0) jn[a] = 0;
     }
-    for (int jk = jlo[2]; jk <= jhi[2]; jk++)
-        for (int jj = jlo[1]; jj <= jhi[1]; jj++)
-            for (int ji = jlo[0]; ji <= jhi[0]; ji++) {
-                const int idj = gidx(gf, ji, jj, jk);
-                const size_t oj = mp * Tf + idj;
-                if (diag_f[oj] == 0.0f) continue;             // column is not an unknown: entries dropped
-                const float pnj = pn_f[oj];
-                if (pnj == 0.0f) continue;
-                double t = 0.0;
+    const int ncol = jn[0] * jn[1] * jn[2];
+    for (int base = 0; base < ncol; base += 32) {
+        // ---- gather: this lane's column
+        const int c = base + lane;
+        double t = 0.0;
+        int ji = 0, jj = 0, jk = 0;
+        float pnj = 0.0f;
+        if (c < ncol) {
+            ji = jlo[0] + c % jn[0]; jj = jlo[1] + (c / jn[0]) % jn[1]; jk = jlo[2] + c / (jn[0] * jn[1]);
+            const int idj = gidx(gf, ji, jj, jk);
+            const size_t oj = mp * Tf + idj;
+            if (diag_f[oj] != 0.0f) pnj = pn_f[oj];       // a column that is not an unknown drops out (pnj stays 0)
+            if (pnj != 0.0f) {
                 if (FINE0) {
                     int off[7][3];
                     double val[7];
@@ -294,7 +291,6 @@ __global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid g
                     }
                 } else {
                     const float *__restrict__ Sj = S_f + (size_t)rowmap_f[oj] * GMG_STRIDE + R.base;
-                    // children i = j + o with o inside the window of row j
                     int a0 = ji + olo[0] - lo[0], a1 = ji + ohi[0] - lo[0];
                     int b0 = jj + olo[1] - lo[1], b1 = jj + ohi[1] - lo[1];
                     int c0 = jk + olo[2] - lo[2], c1 = jk + ohi[2] - lo[2];
@@ -307,10 +303,43 @@ __global__ void __launch_bounds__(GMG_BUILD_THREADS) k_gmg_build(Grid gc, Grid g
                             for (int a = a0; a <= a1; a++) t += (double)wP[(c2 * 4 + b2) * 4 + a] * (double)Sr[a];
                         }
                 }
-                if (t == 0.0) continue;
-                gmg_scatter(acc, W, mp, t / (double)pnj, ji, jj, jk, I, J, K, gc, diag_c);
+                t /= (double)pnj;
             }
-    for (int q = 0; q < W.size; q++) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q][threadIdx.x]);
+        }
+        // ---- this lane's <= 8 contributions (slot, value); slot -1 = none
+        int pi[2], pj[2], pk[2];
+        float wi[2], wj[2], wk[2];
+        vmg_parents(mp == 0, ji, pi[0], pi[1], wi[0], wi[1]);
+        vmg_parents(mp == 1, jj, pj[0], pj[1], wj[0], wj[1]);
+        vmg_parents(mp == 2, jk, pk[0], pk[1], wk[0], wk[1]);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int a = q & 1, b2 = (q >> 1) & 1, c2 = q >> 2;
+            float w = wi[a] * wj[b2] * wk[c2];
+            int PI = pi[a], PJ = pj[b2], PK = pk[c2];
+            int slot = -1;
+            if (t != 0.0 && w != 0.0f && PI >= 0 && PJ >= 0 && PK >= 0 && PI <= gc.ni && PJ <= gc.nj && PK <= gc.nk &&
+                diag_c[(size_t)mp * Tc + gidx(gc, PI, PJ, PK)] != 0.0f) {
+                int oi = PI - I - W.lo[0], oj2 = PJ - J - W.lo[1], ok = PK - K - W.lo[2];
+                if (oi >= 0 && oj2 >= 0 && ok >= 0 && oi < W.n[0] && oj2 < W.n[1] && ok < W.n[2]) slot = (ok * W.n[1] + oj2) * W.n[0] + oi;
+            }
+            sslot[lane * 8 + q] = slot;
+            sval[lane * 8 + q] = t * (double)w;
+        }
+        // ---- ordered scatter: step l applies lane l's contributions, contribution q by lane q
+        const unsigned active = __ballot_sync(0xffffffffu, t != 0.0);
+        __syncwarp();
+        for (int l = 0; l < 32; l++) {
+            if (!((active >> l) & 1u)) continue;      // uniform across the warp
+            if (lane < 8) {
+                int slot = sslot[l * 8 + lane];
+                if (slot >= 0) acc[slot] += sval[l * 8 + lane];
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int q = lane; q < W.size; q += 32) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q]);
 }
 
 // dense diagonal of an explicit level (also its unknown flag) = the (0,0,0) slot of the (m,m) window, and the
@@ -363,10 +392,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
     __shared__ int offs[3][GMG_STRIDE];
     if (st && st->done) return;
     if (MODE != 0) {
-        for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) {
-            int m = q / GMG_STRIDE, slot = q - m * GMG_STRIDE;
-            offs[m][slot] = slot < GMG_SLOTS ? gmg_slot_offset(L.g, m, slot) : 0;
-        }
+        for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
         __syncthreads();
     }
     const int nrows = *L.nrows;
@@ -528,39 +554,39 @@ __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *_
     }
 }
 
-// coarse b = P^T r / 8 (r already divided by pn) and the first sweep from zero, x0 = w b; one thread per coarse row
+// coarse b = P^T r / 8 (r already divided by pn) and the first sweep from zero, x0 = w b.  One warp per coarse
+// row: the <= 48 fine children are spread over the lanes (two per lane), so a row costs one memory round trip
+// instead of 48 serialised ones.
 __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
                                                              float *__restrict__ x0, const CGState *__restrict__ st) {
     if (st && st->done) return;
     const int nrows = *C.nrows;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
         int enc = C.rows[r];
         int m = enc / C.g.total, id = enc - m * C.g.total;
         int I, J, K;
         gmg_unflatten(C.g, id, I, J, K);
         const float *rr = rf + (size_t)m * gf.total;
-        int li, ci, lj, cj, lk, ck;
-        float wi[4], wj[4], wk[4];
-        vmg_axis(m == 0, I, li, ci, wi);
-        vmg_axis(m == 1, J, lj, cj, wj);
-        vmg_axis(m == 2, K, lk, ck, wk);
         float acc = 0.0f;
-        for (int c2 = 0; c2 < ck; c2++) {
-            int fk = lk + c2;
-            if (fk < 0 || fk > gf.nk) continue;
-            for (int b2 = 0; b2 < cj; b2++) {
-                int fj = lj + b2;
-                if (fj < 0 || fj > gf.nj) continue;
-                float wjk = wj[b2] * wk[c2];
-                for (int a = 0; a < ci; a++) {
-                    int fi = li + a;
-                    if (fi < 0 || fi > gf.ni) continue;
-                    acc += wi[a] * wjk * rr[gidx(gf, fi, fj, fk)];
-                }
-            }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            int q = lane + 32 * t;              // child (a, b2, c2) in a 4 x 4 x 4 box, a fastest
+            int a = q & 3, b2 = (q >> 2) & 3, c2 = q >> 4;
+            // along a component's own axis: fine 2I-1, 2I, 2I+1 with 1/2, 1, 1/2; across it: 2J-1 .. 2J+2 with 1/4, 3/4, 3/4, 1/4
+            int fi = 2 * I - 1 + a, fj = 2 * J - 1 + b2, fk = 2 * K - 1 + c2;
+            float wi = m == 0 ? (a == 1 ? 1.0f : (a < 3 ? 0.5f : 0.0f)) : ((a == 1 || a == 2) ? 0.75f : 0.25f);
+            float wj = m == 1 ? (b2 == 1 ? 1.0f : (b2 < 3 ? 0.5f : 0.0f)) : ((b2 == 1 || b2 == 2) ? 0.75f : 0.25f);
+            float wk = m == 2 ? (c2 == 1 ? 1.0f : (c2 < 3 ? 0.5f : 0.0f)) : ((c2 == 1 || c2 == 2) ? 0.75f : 0.25f);
+            float w = wi * wj * wk;
+            if (w != 0.0f && fi >= 0 && fj >= 0 && fk >= 0 && fi <= gf.ni && fj <= gf.nj && fk <= gf.nk) acc += w * rr[gidx(gf, fi, fj, fk)];
         }
-        float bv = 0.125f * acc;
-        bc[enc] = bv;
-        x0[enc] = C.wj[r] * bv;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float bv = 0.125f * acc;
+            bc[enc] = bv;
+            x0[enc] = C.wj[r] * bv;
+        }
     }
 }

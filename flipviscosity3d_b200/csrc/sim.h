@@ -45,7 +45,7 @@ struct Sim {
     int visc_maxit = 700;               // src/viscositysolver.h:202
     int visc_maxit_scale = 40;
     int visc_warm_start = 0;            // start the viscosity CG from the current velocity instead of 0
-    int visc_precond = 0;               // 0 = diagonal (default), 1 = multigrid V-cycle (vmg.h, experimental)
+    int visc_precond = 2;               // 2 = Galerkin multigrid (gmg.h, default), 0 = diagonal, 1 = rediscretised multigrid (vmg.h)
     int mg_sweeps = 2;                  // damped-Jacobi sweeps before = after the coarse correction
     int mg_coarse_sweeps = 24;
     float mg_omega = 0.5f;
@@ -159,6 +159,7 @@ void solve_pressure(Sim &s, float dt);
 void stage_apply_viscosity(Sim &s, float dt);
 void viscosity_volumes(Sim &s);
 void viscosity_free(Sim &s);
+int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_launch, unsigned long long *alg_bytes);
 
 // dist.cu
 void dist_setup_slab(Sim &s);

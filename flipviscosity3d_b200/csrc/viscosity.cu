@@ -484,6 +484,11 @@ static GMG *gmg_get(Sim &s) {
             vmg_dev_alloc(L.blk_flag, (size_t)g.nblocks); vmg_dev_alloc(L.blk_list, (size_t)g.nblocks);
             vmg_dev_alloc(L.blk_count, 1);
             vmg_dev_alloc(L.rows, 3 * T); vmg_dev_alloc(L.rowmap, 3 * T); vmg_dev_alloc(L.nrows_dev, 1);
+            vmg_dev_alloc(L.offs, 3 * GMG_STRIDE);
+            std::vector<int> offs(3 * GMG_STRIDE, 0);
+            for (int m = 0; m < 3; m++)
+                for (int slot = 0; slot < GMG_SLOTS; slot++) offs[m * GMG_STRIDE + slot] = gmg_slot_offset(g, m, slot);
+            CUDA_CHECK(cudaMemcpy(L.offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
             L.owns = true;
         }
         M->nalloc = l + 1;
@@ -503,7 +508,7 @@ static void gmg_free(Sim &s) {
         cudaFree(L.x[0]); cudaFree(L.x[1]); cudaFree(L.r); cudaFree(L.pn);
         if (L.owns) {
             cudaFree(L.diag); cudaFree(L.b); cudaFree(L.blk_flag); cudaFree(L.blk_list); cudaFree(L.blk_count);
-            cudaFree(L.rows); cudaFree(L.rowmap); cudaFree(L.nrows_dev); cudaFree(L.S); cudaFree(L.wj);
+            cudaFree(L.rows); cudaFree(L.rowmap); cudaFree(L.nrows_dev); cudaFree(L.S); cudaFree(L.wj); cudaFree(L.offs);
         }
     }
     cudaFreeHost(M->count_host);
@@ -513,7 +518,7 @@ static void gmg_free(Sim &s) {
 
 static GLevelDev gmg_dev(const GLevel &L) {
     GLevelDev d;
-    d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj;
+    d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
     return d;
 }
 static VLevelDev gmg_vdev(const GLevel &L, const float *coef) {
@@ -574,15 +579,15 @@ static void gmg_build(Sim &s, GMG &M) {
         // transfer normaliser of the fine level, then the Galerkin product
         FLIP_LAUNCH(k_gmg_pnorm, gmg_grid(s, F), CG_THREADS, s.stream, F.g, (const int *)F.blk_list, (const int *)F.blk_count,
                     (const float *)F.diag, L.g, (const float *)L.diag, F.pn);
-        int GB = 3 * cdiv(L.nrows, GMG_BUILD_THREADS);
+        int GB = cdiv(3LL * L.nrows, GMG_BUILD_WARPS);
         if (l == 1) {
             auto kb = &k_gmg_build<true>;
-            FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)s.vcoef, (const int *)nullptr,
                         (const float *)s.vvol, 0);
         } else {
             auto kb = &k_gmg_build<false>;
-            FLIP_LAUNCH(kb, GB, GMG_BUILD_THREADS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)nullptr, (const int *)F.rowmap,
                         (const float *)F.S, F.nrows);
         }
@@ -630,7 +635,7 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         GLevel &L = M.lv[l];
         GLevelDev D = gmg_dev(L);
         int GR = gmg_row_grid(s, L), GT = cdiv(L.nrows, 256);
-        FLIP_LAUNCH(k_gmg_restrict_first, GT, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
+        FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
         int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre;
         for (int k = 1; k < sweeps; k++) {
@@ -746,6 +751,15 @@ void stage_apply_viscosity(Sim &s, float dt) {
     s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0, 0};
     if (!s.viscosity_nonzero) return;  // src/fluidsimulation.cpp:171-184
     const Grid &g = s.g;
+    // The multigrid hierarchy is not slab-decomposed yet: with several ranks every rank runs the whole
+    // (deterministic, hence bit-identical) multigrid solve instead of a slab of the 50x slower Jacobi-PCG.
+    struct Replicated {
+        Sim &s; int nranks, bz0, bz1;
+        Replicated(Sim &sim, bool on) : s(sim), nranks(sim.nranks), bz0(sim.bz0), bz1(sim.bz1) {
+            if (on) { s.nranks = 1; s.bz0 = 0; s.bz1 = s.g.nbz; }
+        }
+        ~Replicated() { s.nranks = nranks; s.bz0 = bz0; s.bz1 = bz1; }
+    } replicated(s, s.visc_precond == 2 && s.nranks > 1);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
@@ -911,5 +925,58 @@ extern "C" int flip_debug_gmg_level(void *hsim, int level, int *info /*[10]: ni,
     if (rows_out && cudaMemcpy(rows_out, L.rows, (size_t)L.nrows * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
     if (S_out && cudaMemcpy(S_out, L.S, (size_t)L.nrows * GMG_STRIDE * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
     if (diag_out && cudaMemcpy(diag_out, L.diag, 3 * (size_t)g.total * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -4;
+    return 0;
+}
+
+// Average duration (CUDA events on the library's stream) of `reps` back-to-back launches of a hot kernel on the
+// hierarchy of the last viscosity solve, and its algorithmic bytes per launch:
+//   "gmg_sweep_l1"  one damped-Jacobi sweep on the first explicit level: rows x (235 coefficients + row index +
+//                   weight + b + x in + x out) x 4 B
+//   "visc_apply"    the level-0 matrix-free stencil apply of the CG (120 B per unknown share of SURVEY 8d: 2 vector
+//                   transfers x 8 B + 16 B coefficients per unknown)
+int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_launch, unsigned long long *alg_bytes) {
+    std::string n(name ? name : "");
+    if (reps < 1) reps = 1;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    if (n == "gmg_sweep_l1") {
+        GMG *M = (GMG *)s.gmg;
+        if (!M || M->nlevels < 2 || M->lv[1].nrows == 0) return -1;
+        GLevel &L = M->lv[1];
+        GLevelDev D = gmg_dev(L);
+        auto sweep1 = &k_gmg_sweep<1>;
+        int GR = gmg_row_grid(s, L);
+        const float *nof = nullptr;
+        FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[0], L.x[1], nof, M->omega, (const CGState *)nullptr);
+        CUDA_CHECK(cudaEventRecord(e0, s.stream));
+        for (int k = 0; k < reps; k++)
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
+        CUDA_CHECK(cudaEventRecord(e1, s.stream));
+        *alg_bytes = (unsigned long long)L.nrows * (GMG_SLOTS + 5) * 4ull;
+    } else if (n == "visc_apply") {
+        if (s.visc_stats.unknowns == 0) return -1;
+        CGParams P;
+        P.g = s.g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
+        P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
+        P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
+        CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
+        int G = cg_grid(s);
+        FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
+        CUDA_CHECK(cudaEventRecord(e0, s.stream));
+        for (int k = 0; k < reps; k++)
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
+        CUDA_CHECK(cudaEventRecord(e1, s.stream));
+        *alg_bytes = (unsigned long long)s.visc_stats.unknowns * (2 * 8 + 16);
+    } else {
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return -2;
+    }
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    KERNEL_CHECK();
+    s.kernel_launches += reps + 1;
+    *ms_per_launch = ms / reps;
     return 0;
 }

@@ -219,6 +219,12 @@ class FlipSim:
     def set_param(self, name, value):
         self._ck(self.lib.flip_set_param(self.h, name.encode(), C.c_double(value)))
 
+    def time_kernel(self, name, reps=20):
+        """(ms per launch, algorithmic bytes per launch) of a named hot kernel on the last solve's data."""
+        ms, nb = C.c_float(), C.c_uint64()
+        self._ck(self.lib.flip_time_kernel(self.h, name.encode(), int(reps), C.byref(ms), C.byref(nb)))
+        return float(ms.value), int(nb.value)
+
     def stats(self):
         st = _lib.flip_stats()
         self._ck(self.lib.flip_get_stats(self.h, C.byref(st)))
