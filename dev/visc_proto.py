@@ -335,11 +335,12 @@ class MG:
             if self.coarse_exact:
                 return self.lu.solve(r)
             return self.smooth(l, None, r, 30)
-        x = self.smooth(l, None, r, self.pre)
+        npre = self.pre_levels[l] if getattr(self, "pre_levels", None) else self.pre
+        x = self.smooth(l, None, r, npre)
         res = r - self.A[l] @ x
         xc = self.vcycle(self.R[l] @ res, l + 1)
         x = x + self.alpha * (self.P[l] @ xc)
-        x = self.smooth(l, x, r, self.pre)
+        x = self.smooth(l, x, r, npre)
         return x
 
 

@@ -547,6 +547,8 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_levels") s.mg_levels = (int)value;
     else if (n == "mg_flexible") s.mg_flexible = (int)value;
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
+    else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;
+    else if (n == "mg_sweeps_l1") s.mg_sweeps_l1 = (int)value;
     else if (n == "pic_ratio") s.pic_ratio = (float)value;
     else if (n == "cfl") { s.cfl_number = (float)value; s.extrap_layers = (int)ceil(s.cfl_number) + 2; }
     else if (n == "verbose") s.verbose = (int)value;

@@ -66,8 +66,12 @@ struct GMG {
     int nlevels = 0, nalloc = 0;
     GLevel lv[GMG_MAX_LEVELS];
     int pre = 2, coarse_sweeps = 24;
+    int pre_l[GMG_MAX_LEVELS] = {2, 1, 2, 2, 2, 2, 2, 2};   // sweeps before = after the coarse correction, per level
     float omega = 0.5f;
     int *count_host = 0;  // pinned
+    void *exec = 0;       // cudaGraphExec_t of one chunk of multigrid-PCG iterations
+    unsigned long long exec_sig = 0;
+    long long exec_launches = 0;
 };
 
 struct GLevelDev {

@@ -512,6 +512,9 @@ static void gmg_free(Sim &s) {
         }
     }
     cudaFreeHost(M->count_host);
+#ifndef FLIP_CPU_EMU
+    if (M->exec) cudaGraphExecDestroy((cudaGraphExec_t)M->exec);
+#endif
     delete M;
     s.gmg = nullptr;
 }
@@ -531,13 +534,18 @@ static int gmg_grid(const Sim &s, const GLevel &L) {
     return L.g.nblocks < G ? L.g.nblocks : G;
 }
 static int gmg_row_grid(const Sim &s, const GLevel &L) {
-    int G = cdiv(L.nrows, 8), cap = s.num_sms * 8;   // one warp per row, 8 warps per CTA
-    return G < 1 ? 1 : (G > cap ? cap : G);
+    // one warp per row, 8 warps per CTA.  Sized from the row CAPACITY (which only changes when the level is
+    // re-allocated), not the row count of this solve, so the captured launch sequence stays valid across solves.
+    long long G = cdiv((long long)L.cap, 8), cap = s.num_sms * 8;
+    return (int)(G < 1 ? 1 : (G > cap ? cap : G));
 }
 
 // Galerkin operators for this solve: unknown flags, row lists, transfer normalisers, A_c = P^T A P / 8
 static void gmg_build(Sim &s, GMG &M) {
     M.pre = s.mg_sweeps < 1 ? 1 : s.mg_sweeps;
+    for (int l = 0; l < GMG_MAX_LEVELS; l++) M.pre_l[l] = M.pre;
+    if (s.mg_sweeps_l0 > 0) M.pre_l[0] = s.mg_sweeps_l0;
+    if (s.mg_sweeps_l1 > 0) M.pre_l[1] = s.mg_sweeps_l1;
     M.coarse_sweeps = s.mg_coarse_sweeps;
     M.omega = s.mg_omega;
     int want = s.mg_levels < M.nalloc ? (s.mg_levels < 1 ? 1 : s.mg_levels) : M.nalloc;
@@ -616,28 +624,28 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
     FLIP_LAUNCH(l0_first, G0, 256, s.stream, P0, r_in, nof, L0.x[0], (double *)nullptr, w, st);
     cur[0] = 0;
     if (last == 0) {
-        for (int k = 1; k < 2 * M.pre - 1; k++) {
+        for (int k = 1; k < 2 * M.pre_l[0] - 1; k++) {
             FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
             cur[0] ^= 1;
         }
         FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
-        s.kernel_launches += 2 * M.pre;
+        s.kernel_launches += 2 * M.pre_l[0];
         return;
     }
-    for (int k = 1; k < M.pre; k++) {
+    for (int k = 1; k < M.pre_l[0]; k++) {
         FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
         cur[0] ^= 1;
     }
     FLIP_LAUNCH(l0_resid, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.r, (double *)nullptr, w, st);
-    s.kernel_launches += M.pre + 1;
+    s.kernel_launches += M.pre_l[0] + 1;
     // explicit levels, downstroke
     for (int l = 1; l <= last; l++) {
         GLevel &L = M.lv[l];
         GLevelDev D = gmg_dev(L);
-        int GR = gmg_row_grid(s, L), GT = cdiv(L.nrows, 256);
+        int GR = gmg_row_grid(s, L);
         FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
-        int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre;
+        int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre_l[l];
         for (int k = 1; k < sweeps; k++) {
             FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
@@ -649,21 +657,21 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
     for (int l = last - 1; l >= 1; l--) {
         GLevel &L = M.lv[l];
         GLevelDev D = gmg_dev(L);
-        int GR = gmg_row_grid(s, L), GT = cdiv(L.nrows, 256);
+        int GR = gmg_row_grid(s, L), GT = cdiv((long long)L.cap, 256) < s.num_sms * 8 ? cdiv((long long)L.cap, 256) : s.num_sms * 8;
         FLIP_LAUNCH(k_gmg_prolong, GT, 256, s.stream, D, (const float *)L.pn, M.lv[l + 1].g, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], st);
-        for (int k = 0; k < M.pre; k++) {
+        for (int k = 0; k < M.pre_l[l]; k++) {
             FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
         }
-        s.kernel_launches += 1 + M.pre;
+        s.kernel_launches += 1 + M.pre_l[l];
     }
     FLIP_LAUNCH(k_gmg0_prolong, G0, 256, s.stream, P0, M.lv[1].g, (const float *)M.lv[1].x[cur[1]], L0.x[cur[0]], st);
-    for (int k = 0; k < M.pre - 1; k++) {
+    for (int k = 0; k < M.pre_l[0] - 1; k++) {
         FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
         cur[0] ^= 1;
     }
     FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
-    s.kernel_launches += 1 + M.pre;
+    s.kernel_launches += 1 + M.pre_l[0];
 }
 
 // Multigrid-preconditioned CG: cg.h's run_cg_mg with the iteration chunk (stencil apply, update, V-cycle, dot,
@@ -700,16 +708,35 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         per_chunk = s.kernel_launches - before;
     };
 #ifndef FLIP_CPU_EMU
+    // The graph is keyed by everything the launch sequence depends on (level count, sweep counts, every pointer
+    // and capacity-derived grid size); row counts are read on the device.  It is re-captured only when a level
+    // was re-allocated or a parameter changed, typically once per simulation.
     cudaGraphExec_t exec = nullptr;
     if (s.use_graphs) {
-        cudaGraph_t graph = nullptr;
-        long long keep = s.kernel_launches;
-        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-        launch_chunk();
-        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
-        s.kernel_launches = keep;   // captured, not launched
-        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-        CUDA_CHECK(cudaGraphDestroy(graph));
+        unsigned long long sig = 1469598103934665603ull;
+        auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+        mix((unsigned long long)M.nlevels); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
+        mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
+        for (int l = 0; l < M.nlevels; l++) {
+            const GLevel &L = M.lv[l];
+            mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
+            mix((unsigned long long)(size_t)L.wj); mix((unsigned long long)(size_t)L.x[0]);
+        }
+        if (M.exec && M.exec_sig != sig) { cudaGraphExecDestroy((cudaGraphExec_t)M.exec); M.exec = nullptr; }
+        if (!M.exec) {
+            cudaGraph_t graph = nullptr;
+            long long keep = s.kernel_launches;
+            CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+            launch_chunk();
+            CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+            s.kernel_launches = keep;   // captured, not launched
+            cudaGraphExec_t e = nullptr;
+            CUDA_CHECK(cudaGraphInstantiate(&e, graph, 0));
+            CUDA_CHECK(cudaGraphDestroy(graph));
+            M.exec = (void *)e; M.exec_sig = sig; M.exec_launches = per_chunk;
+        }
+        exec = (cudaGraphExec_t)M.exec;
+        per_chunk = M.exec_launches;
     }
 #endif
     CGState h;
@@ -728,9 +755,6 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         KERNEL_CHECK();
         launched += chunk;
     }
-#ifndef FLIP_CPU_EMU
-    if (exec) cudaGraphExecDestroy(exec);
-#endif
     return h;
 }
 
