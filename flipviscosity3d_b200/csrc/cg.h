@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
     if (parity >= 0 && P.st[parity].done) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
+    // at start-up (parity < 0) there is no q yet, and the fourth partial array still holds max|r0| of a warm start
+    const bool flex = P.flexible && parity >= 0;
     double rz = 0.0, qz = 0.0;
     for (int qq = blockIdx.x * CG_THREADS + threadIdx.x; qq < nc; qq += gridDim.x * CG_THREADS) {
         int id = P.cell_list[qq];
@@ -239,19 +241,21 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
             size_t o = (size_t)m * g.total + id;
             double z = P.z[o];
             rz += P.r[o] * z;
-            if (P.flexible) qz += P.q[o] * z;
+            if (flex) qz += P.q[o] * z;
         }
     }
     rz = cta_reduce<false>(rz, sm);
-    if (P.flexible) qz = cta_reduce<false>(qz, sm);
+    if (flex) qz = cta_reduce<false>(qz, sm);
     if (threadIdx.x == 0) {
         P.part[gridDim.x + blockIdx.x] = rz;
-        if (P.flexible) P.part[3 * gridDim.x + blockIdx.x] = qz;
+        if (flex) P.part[3 * gridDim.x + blockIdx.x] = qz;
     }
 }
 
 // multigrid mode, start-up: x = 0, r = masked b, partial max|b|   (then V-cycle, k_cg_dot, k_cg_start)
-template <int NC, class Diag>
+// KEEPX (warm start): x and r = b - A x0 are already in place (k_cg_guess_residual); only max|r0| is reduced, into
+// the fourth partial array, because the tolerance stays relative to max|b| (k_cg_bmax).
+template <int NC, class Diag, bool KEEPX = false>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
     const Grid &g = P.g;
@@ -263,12 +267,12 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag
             size_t o = (size_t)m * g.total + id;
             double r = diag(m, id) != 0.0f ? P.r[o] : 0.0;
             P.r[o] = r;
-            P.x[o] = 0.0;
+            if (!KEEPX) P.x[o] = 0.0;
             bm = fmax(bm, fabs(r));
         }
     }
     bm = cta_reduce<true>(bm, sm);
-    if (threadIdx.x == 0) P.part[2 * gridDim.x + blockIdx.x] = bm;
+    if (threadIdx.x == 0) P.part[(KEEPX ? 3 : 2) * gridDim.x + blockIdx.x] = bm;
 }
 
 template <int NC>

@@ -678,18 +678,33 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
 // direction: ~70 launches per iteration) replayed from a CUDA graph that is re-captured for every solve, because
 // row counts and (after a re-allocation) pointers of the hierarchy change from solve to solve.
 template <class ApplyFn>
-static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double tol_rel, int maxit, ApplyFn apply) {
+static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double tol_rel, int maxit, ApplyFn apply,
+                          const float *guess) {
     int G = cg_grid(s);
-    auto kinit = &k_cg_init_mg<3, DiagViscosity>;
+    auto kinit = &k_cg_init_mg<3, DiagViscosity, false>;
+    auto kinit_keep = &k_cg_init_mg<3, DiagViscosity, true>;
     auto kstart = &k_cg_start_mg<3>;
     auto kdot = &k_cg_dot<3, DiagViscosity>;
     auto kupdate = &k_cg_update<3, DiagViscosity, true>;
     auto kdir = &k_cg_direction<3, DiagViscosity, true>;
-    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
+    if (guess) {
+        // warm start from the current velocity: r0 = b - A x0; the stopping rule stays max|r| <= tol * max|b|
+        auto kguess = &k_cg_guess<3, DiagViscosity>;
+        auto kres = &k_cg_guess_residual<3, DiagViscosity>;
+        auto kbmax = &k_cg_bmax<3, DiagViscosity>;
+        FLIP_LAUNCH_SYNC(kbmax, G, CG_THREADS, s.stream, P, diag);
+        FLIP_LAUNCH(kguess, G, CG_THREADS, s.stream, P, diag, guess);
+        CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));   // the stencil kernel tests st[0].done
+        apply(0);
+        FLIP_LAUNCH(kres, G, CG_THREADS, s.stream, P, diag);
+        FLIP_LAUNCH_SYNC(kinit_keep, G, CG_THREADS, s.stream, P, diag);
+        s.kernel_launches += 4;
+    } else
+        FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
     gmg_vcycle(s, M, (const double *)P.r, P.z, nullptr);
     FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, -1);
     FLIP_LAUNCH(kstart, G, CG_THREADS, s.stream, P);
-    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, 0.0, tol_rel, maxit, 0);
+    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, 0.0, tol_rel, maxit, guess ? 1 : 0);
     s.kernel_launches += 4;
     KERNEL_CHECK();
     int chunk = s.mg_chunk < 2 ? 2 : (s.mg_chunk & ~1);
@@ -814,7 +829,8 @@ void stage_apply_viscosity(Sim &s, float dt) {
         P.z = s.cg_z;
         P.flexible = s.mg_flexible;
         h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit,
-                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); });
+                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); },
+                       s.visc_warm_start ? (const float *)s.vel : nullptr);
     } else if (s.visc_precond == 1 && s.nranks == 1) {
         VMG *M = vmg_get(s);
         vmg_build(s, *M);
