@@ -547,6 +547,8 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_levels") s.mg_levels = (int)value;
     else if (n == "mg_flexible") s.mg_flexible = (int)value;
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
+    else if (n == "mg_dense") s.mg_dense = (int)value;
+    else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;
     else if (n == "mg_sweeps_l1") s.mg_sweeps_l1 = (int)value;
     else if (n == "pic_ratio") s.pic_ratio = (float)value;

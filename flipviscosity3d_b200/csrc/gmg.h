@@ -69,6 +69,9 @@ struct GMG {
     int pre_l[GMG_MAX_LEVELS] = {2, 1, 2, 2, 2, 2, 2, 2};   // sweeps before = after the coarse correction, per level
     float omega = 0.5f;
     int *count_host = 0;  // pinned
+    double *dense = 0;    // [GMG_DENSE_MAX^2] scratch of the dense inversion
+    float *Ainv = 0;      // [GMG_DENSE_MAX^2] inverse of the coarsest operator
+    bool dense_last = false;
     void *exec = 0;       // cudaGraphExec_t of one chunk of multigrid-PCG iterations
     unsigned long long exec_sig = 0;
     long long exec_launches = 0;
@@ -592,5 +595,70 @@ __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf
             bc[enc] = bv;
             x0[enc] = C.wj[r] * bv;
         }
+    }
+}
+
+// ---- coarsest level: dense inverse -------------------------------------------------------------
+// The hierarchy stops at the first level with <= mg_dense_rows (128) rows - the 4^3 level, 50 rows at 256^3 - and
+// solves it exactly with a dense inverse computed once per solve: one launch per V-cycle instead of 25
+// latency-bound sweeps, and an exact (hence symmetric) coarse solve.
+#define GMG_DENSE_MAX 512
+
+// single CTA: dense A (fp64, symmetrised) from the stored rows, in-place Gauss-Jordan inversion (A is SPD: no
+// pivoting), result as fp32
+__global__ void __launch_bounds__(1024) k_gmg_dense_inverse(GLevelDev L, const int *__restrict__ rowmap, double *__restrict__ D,
+                                                             float *__restrict__ Ainv) {
+    const int n = *L.nrows;
+    const int T = L.g.total;
+    for (int q = threadIdx.x; q < n * n; q += blockDim.x) D[q] = 0.0;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n * GMG_SLOTS; q += blockDim.x) {
+        int r = q / GMG_SLOTS, slot = q - r * GMG_SLOTS;
+        float v = L.S[(size_t)r * GMG_STRIDE + slot];
+        if (v == 0.0f) continue;
+        int enc = L.rows[r];
+        int m = enc / T, id = enc - m * T;
+        int c = rowmap[id + L.offs[m * GMG_STRIDE + slot]];
+        if (c >= 0) D[r * n + c] = (double)v;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n * n; q += blockDim.x) {       // symmetrise (P^T A P is symmetric up to rounding)
+        int i = q / n, j = q - i * n;
+        if (i < j) { double a = 0.5 * (D[i * n + j] + D[j * n + i]); D[i * n + j] = a; D[j * n + i] = a; }
+    }
+    __syncthreads();
+    __shared__ double prow[GMG_DENSE_MAX], pcol[GMG_DENSE_MAX];
+    for (int k = 0; k < n; k++) {
+        const double p = 1.0 / D[k * n + k];
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            prow[j] = j == k ? p : D[k * n + j] * p;
+            pcol[j] = j == k ? 0.0 : D[j * n + k];
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < n * n; q += blockDim.x) {
+            int i = q / n, j = q - i * n;
+            double v;
+            if (i == k) v = prow[j];
+            else if (j == k) v = -pcol[i] * p;
+            else v = D[q] - pcol[i] * prow[j];
+            D[q] = v;
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < n * n; q += blockDim.x) Ainv[q] = (float)D[q];
+}
+
+// x = A^-1 b on the coarsest level, one warp per row
+__global__ void __launch_bounds__(256) k_gmg_dense_apply(GLevelDev L, const float *__restrict__ Ainv, const float *__restrict__ b,
+                                                          float *__restrict__ x, const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    const int n = *L.nrows;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
+        float acc = 0.0f;
+        for (int j = lane; j < n; j += 32) acc += Ainv[i * n + j] * b[L.rows[j]];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) x[L.rows[i]] = acc;
     }
 }

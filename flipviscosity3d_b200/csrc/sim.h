@@ -57,6 +57,8 @@ struct Sim {
     // coefficients per row, 8x fewer rows than level 0's matrix-free stencil): ONE sweep there and two everywhere
     // else costs no iterations (scipy prototype: 32 vs 31 at 128^3) and halves the level-1 traffic.
     int mg_sweeps_l0 = 3, mg_sweeps_l1 = 1;
+    int mg_dense = 1;                   // exact dense solve on the first level with <= mg_dense_rows rows (else Jacobi sweeps there)
+    int mg_dense_rows = 128;            // single-CTA Gauss-Jordan: 0.3 ms at 128 rows, 7 ms at 304 (measured) - keep it small
     int mg_chunk = 8;                   // multigrid CG iterations per graph replay / host convergence poll
     int mg_flexible = 1;                // Polak-Ribiere beta in the multigrid-preconditioned CG
     int cg_chunk = 32;

@@ -467,6 +467,8 @@ static GMG *gmg_get(Sim &s) {
     GMG *M = new GMG();
     s.gmg = M;
     CUDA_CHECK(cudaMallocHost((void **)&M->count_host, 4 * sizeof(int)));
+    vmg_dev_alloc(M->dense, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
+    vmg_dev_alloc(M->Ainv, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
     Grid g = s.g;
     for (int l = 0; l < GMG_MAX_LEVELS; l++) {
         GLevel &L = M->lv[l];
@@ -512,6 +514,7 @@ static void gmg_free(Sim &s) {
         }
     }
     cudaFreeHost(M->count_host);
+    cudaFree(M->dense); cudaFree(M->Ainv);
 #ifndef FLIP_CPU_EMU
     if (M->exec) cudaGraphExecDestroy((cudaGraphExec_t)M->exec);
 #endif
@@ -550,6 +553,7 @@ static void gmg_build(Sim &s, GMG &M) {
     M.omega = s.mg_omega;
     int want = s.mg_levels < M.nalloc ? (s.mg_levels < 1 ? 1 : s.mg_levels) : M.nalloc;
     M.nlevels = 1;
+    M.dense_last = false;
     for (int l = 0; l < want; l++) {
         GLevel &L = M.lv[l];
         size_t T = (size_t)L.g.total;
@@ -602,6 +606,14 @@ static void gmg_build(Sim &s, GMG &M) {
         FLIP_LAUNCH_SYNC(k_gmg_diag, cdiv(L.nrows, 8), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const float *)L.S, L.diag, L.wj, M.omega);
         s.kernel_launches += 3;
         M.nlevels = l + 1;
+        if (s.mg_dense && L.nrows <= (s.mg_dense_rows < GMG_DENSE_MAX ? s.mg_dense_rows : GMG_DENSE_MAX)) {
+            // small enough for an exact solve: this is the last level
+            GLevelDev D = gmg_dev(L);
+            FLIP_LAUNCH_SYNC(k_gmg_dense_inverse, 1, 1024, s.stream, D, (const int *)L.rowmap, M.dense, M.Ainv);
+            s.kernel_launches++;
+            M.dense_last = true;
+            break;
+        }
     }
     KERNEL_CHECK();
 }
@@ -645,6 +657,11 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         int GR = gmg_row_grid(s, L);
         FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
+        if (l == last && M.dense_last) {
+            FLIP_LAUNCH_SYNC(k_gmg_dense_apply, 8, 256, s.stream, D, (const float *)M.Ainv, (const float *)L.b, L.x[0], st);
+            s.kernel_launches += 2;
+            continue;
+        }
         int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre_l[l];
         for (int k = 1; k < sweeps; k++) {
             FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
@@ -730,7 +747,7 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
     if (s.use_graphs) {
         unsigned long long sig = 1469598103934665603ull;
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
-        mix((unsigned long long)M.nlevels); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
+        mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
