@@ -62,6 +62,8 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s.vvalid, T);
     dev_alloc(s.vcoef, 4 * T);
     dev_alloc(s.vdiag, 3 * T);
+    dev_alloc(s.ext_flag, (size_t)g.nblocks); dev_alloc(s.ext_flag2, (size_t)g.nblocks);
+    dev_alloc(s.ext_list, (size_t)g.nblocks); dev_alloc(s.ext_count, 1);
     dev_alloc(s.blk_flag, (size_t)g.nblocks);
     dev_alloc(s.blk_list, (size_t)g.nblocks);
     dev_alloc(s.blk_count, 1);
@@ -115,7 +117,8 @@ void sim_free(Sim &s) {
     void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
                     s.weight, s.valid, s.layer, s.fstate, s.viscosity, s.pressure, s.maxvel_dev, s.pcoef, s.cg_x,
                     s.cg_r, s.cg_s, s.cg_q, s.cg_z, s.cg_w, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
-                    s.blk_count, s.unk_count, s.cell_list, s.cell_count, s.part, s.cgst};
+                    s.blk_count, s.unk_count, s.cell_list, s.cell_count, s.part, s.cgst, s.ext_flag, s.ext_flag2, s.ext_list,
+                    s.ext_count};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
     if (s.count_host) cudaFreeHost(s.count_host);

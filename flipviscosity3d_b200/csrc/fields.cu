@@ -8,7 +8,7 @@
 //   apply pressure     src/fluidsimulation.cpp:598-688
 //   constrain          src/fluidsimulation.cpp:696-729
 //   CFL                src/fluidsimulation.cpp:241-269
-#include "sim.h"
+#include "cg.h"
 #include "levelset_math.h"
 
 // ------------------------------------------------------------------------------------------
@@ -99,63 +99,104 @@ void stage_add_body_force(Sim &s, float dt) {
 #define LAYER_DONE 254
 #define LAYER_UNKNOWN 255
 
-__global__ void k_extrap_init(Grid g, const unsigned char *__restrict__ valid, unsigned char *__restrict__ layer) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
-    int id = gidx(g, i, j, k);
-    size_t T = (size_t)g.total;
-    for (int c = 0; c < 3; c++) {
-        int w = g.ni + (c == 0), h = g.nj + (c == 1), d = g.nk + (c == 2);
-        if (i >= w || j >= h || k >= d) continue;
-        bool border = i == 0 || j == 0 || k == 0 || i == w - 1 || j == h - 1 || k == d - 1;
-        layer[c * T + id] = valid[c * T + id] ? 0 : (border ? LAYER_DONE : LAYER_UNKNOWN);
+// Block-shaped (one CTA per 8x8x8 block) so that the same pass also flags the blocks that hold a valid face:
+// the layers only ever reach faces within `layers` <= 8 cells of a valid one, i.e. inside the 26-neighbourhood
+// of a flagged block, and the layer kernels then run over that block list (~10 % of the 256^3 grid) instead of
+// sweeping the whole grid 14 times per substep.
+__global__ void __launch_bounds__(CG_THREADS) k_extrap_init(Grid g, const unsigned char *__restrict__ valid, unsigned char *__restrict__ layer,
+                                                             int *__restrict__ flag) {
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    BlockCell bc = block_cell(g, blockIdx.x, threadIdx.x);
+    bool has = false;
+    if (bc.inside) {
+        const int i = bc.i, j = bc.j, k = bc.k;
+        int id = gidx(g, i, j, k);
+        size_t T = (size_t)g.total;
+        for (int c = 0; c < 3; c++) {
+            int w = g.ni + (c == 0), h = g.nj + (c == 1), d = g.nk + (c == 2);
+            if (i >= w || j >= h || k >= d) continue;
+            bool border = i == 0 || j == 0 || k == 0 || i == w - 1 || j == h - 1 || k == d - 1;
+            bool v = valid[c * T + id] != 0;
+            has = has || v;
+            layer[c * T + id] = v ? 0 : (border ? LAYER_DONE : LAYER_UNKNOWN);
+        }
     }
+    if (has) any = 1;  // benign same-value race
+    __syncthreads();
+    if (threadIdx.x == 0) flag[blockIdx.x] = any;
 }
 
-__global__ void __launch_bounds__(256) k_extrap_layer(Grid g, float *__restrict__ vel, unsigned char *__restrict__ layer, int L) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
-    int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
-    size_t T = (size_t)g.total;
-    for (int c = 0; c < 3; c++) {
-        int w = g.ni + (c == 0), h = g.nj + (c == 1), d = g.nk + (c == 2);
-        if (i >= w || j >= h || k >= d) continue;
-        unsigned char *ly = layer + c * T;
-        if (ly[id] != LAYER_UNKNOWN) continue;
-        // an UNKNOWN cell is never on the border (those are DONE), so all six neighbours exist
-        float *f = vel + c * T;
-        const int off[6] = {-1, 1, -sy, sy, -sz, sz};
-        const int ii[6] = {i - 1, i + 1, i, i, i, i};
-        const int jj[6] = {j, j, j - 1, j + 1, j, j};
-        const int kk[6] = {k, k, k, k, k - 1, k + 1};
-        float sum = 0.0f;
-        int count = 0;
-        bool reached = false;
-        for (int n = 0; n < 6; n++) {
-            if (ly[id + off[n]] < L) {  // KNOWN at the start of this layer
-                sum += f[id + off[n]];
-                count++;
-                // only KNOWN cells with interior indices push the front (loop bounds 1..dim-2,
-                // src/macvelocityfield.cpp:604-606)
-                if (ii[n] >= 1 && ii[n] <= w - 2 && jj[n] >= 1 && jj[n] <= h - 2 && kk[n] >= 1 && kk[n] <= d - 2)
-                    reached = true;
+// flag2[b] = any flagged block in the 26-neighbourhood of b
+__global__ void __launch_bounds__(256) k_extrap_dilate(Grid g, const int *__restrict__ flag, int *__restrict__ flag2) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.nblocks) return;
+    int bi = b % g.nbx, r = b / g.nbx;
+    int bj = r % g.nby, bk = r / g.nby;
+    int any = 0;
+    for (int c = -1; c <= 1; c++)
+        for (int bb = -1; bb <= 1; bb++)
+            for (int a = -1; a <= 1; a++) {
+                int x = bi + a, y = bj + bb, z = bk + c;
+                if (x < 0 || y < 0 || z < 0 || x >= g.nbx || y >= g.nby || z >= g.nbz) continue;
+                any |= flag[x + g.nbx * (y + g.nby * z)];
             }
-        }
-        if (reached) {
-            f[id] = sum / (float)count;
-            ly[id] = (unsigned char)L;
+    flag2[b] = any;
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_extrap_layer(Grid g, const int *__restrict__ list, const int *__restrict__ count,
+                                                              float *__restrict__ vel, unsigned char *__restrict__ layer, int L) {
+    const int nb = *count;
+    const int sy = SY(g), sz = SZ(g);
+    const size_t T = (size_t)g.total;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        BlockCell bc = block_cell(g, list[b], threadIdx.x);
+        if (!bc.inside) continue;
+        const int i = bc.i, j = bc.j, k = bc.k;
+        int id = gidx(g, i, j, k);
+        for (int c = 0; c < 3; c++) {
+            int w = g.ni + (c == 0), h = g.nj + (c == 1), d = g.nk + (c == 2);
+            if (i >= w || j >= h || k >= d) continue;
+            unsigned char *ly = layer + c * T;
+            if (ly[id] != LAYER_UNKNOWN) continue;
+            // an UNKNOWN cell is never on the border (those are DONE), so all six neighbours exist
+            float *f = vel + c * T;
+            const int off[6] = {-1, 1, -sy, sy, -sz, sz};
+            const int ii[6] = {i - 1, i + 1, i, i, i, i};
+            const int jj[6] = {j, j, j - 1, j + 1, j, j};
+            const int kk[6] = {k, k, k, k, k - 1, k + 1};
+            float sum = 0.0f;
+            int cnt = 0;
+            bool reached = false;
+            for (int n = 0; n < 6; n++) {
+                if (ly[id + off[n]] < L) {  // KNOWN at the start of this layer
+                    sum += f[id + off[n]];
+                    cnt++;
+                    // only KNOWN cells with interior indices push the front (loop bounds 1..dim-2,
+                    // src/macvelocityfield.cpp:604-606)
+                    if (ii[n] >= 1 && ii[n] <= w - 2 && jj[n] >= 1 && jj[n] <= h - 2 && kk[n] >= 1 && kk[n] <= d - 2)
+                        reached = true;
+                }
+            }
+            if (reached) {
+                f[id] = sum / (float)cnt;
+                ly[id] = (unsigned char)L;
+            }
         }
     }
 }
 
 void extrapolate_velocity(Sim &s) {
     const Grid &g = s.g;
-    long long nf = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
-    FLIP_LAUNCH(k_extrap_init, cdiv(nf, 256), 256, s.stream, g, (const unsigned char *)s.valid, s.layer);
+    FLIP_LAUNCH_SYNC(k_extrap_init, g.nblocks, CG_THREADS, s.stream, g, (const unsigned char *)s.valid, s.layer, s.ext_flag);
+    FLIP_LAUNCH(k_extrap_dilate, cdiv(g.nblocks, 256), 256, s.stream, g, (const int *)s.ext_flag, s.ext_flag2);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.ext_flag2, g.nblocks, s.ext_list, s.ext_count, 0, g.nblocks);
+    int G = s.num_sms * 4 < g.nblocks ? s.num_sms * 4 : g.nblocks;
     for (int L = 1; L <= s.extrap_layers; L++) {
-        FLIP_LAUNCH(k_extrap_layer, cdiv(nf, 256), 256, s.stream, g, s.vel, s.layer, L);
+        FLIP_LAUNCH(k_extrap_layer, G, CG_THREADS, s.stream, g, (const int *)s.ext_list, (const int *)s.ext_count, s.vel, s.layer, L);
     }
-    s.kernel_launches += 1 + s.extrap_layers;
+    s.kernel_launches += 3 + s.extrap_layers;
     KERNEL_CHECK();
 }
 

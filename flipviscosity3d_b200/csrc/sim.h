@@ -113,6 +113,7 @@ struct Sim {
     unsigned char *vvalid = 0;// dilated liquid mask
     float *vcoef = 0;         // 4 coefficient grids [4*total]: center, edgeU, edgeV, edgeW
     float *vdiag = 0;         // [3*total] row diagonals (0 = not an unknown)
+    int *ext_flag = 0, *ext_flag2 = 0, *ext_list = 0, *ext_count = 0;   // extrapolation block list [nblocks] x3, [1]
     int *blk_flag = 0;        // [nblocks]
     int *blk_list = 0;        // [nblocks]
     int *blk_count = 0;       // [1]
