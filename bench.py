@@ -153,7 +153,7 @@ def run_reference(args):
 def workload_config(args, particles):
     return {"workload": "bunny_in_sphere_%d^3_8ppc_viscosity%g (BASELINE.json configs[3])" % (args.size, args.viscosity),
             "grid": [args.size] * 3, "particles": int(particles), "viscosity": args.viscosity, "frame_dt": FRAME_DT,
-            "step": "one substep of FluidSimulation::advance", "parallelism": "x%d: pressure CG k-slab decomposed (exchanges over %s); multigrid viscosity solve and particle/grid stages replicated" % (args.gpus, "NCCL" if getattr(args, "no_p2p", False) else "peer memory over NVLink"),
+            "step": "one substep of FluidSimulation::advance", "parallelism": "x%d: every rank runs the whole substep (multigrid viscosity solve not decomposed; pressure CG k-slab decomposed over %s only above 1 M unknowns per rank: 0.62 M here)" % (args.gpus, "NCCL" if getattr(args, "no_p2p", False) else "peer memory"),
             "viscosity_solver": "PCG, Galerkin multigrid V-cycle preconditioner, 3/1/2 sweeps on level 0/1/deeper (viscosity_precond=%d)" % getattr(args, "precond", 2),
             "l2": "working set (fields, CG vectors, 280 MB of level-1 multigrid coefficients) exceeds the 126 MB L2; no flush between steps"}
 

@@ -105,6 +105,18 @@ __global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const 
 
 void solve_pressure(Sim &s, float dt) {
     const Grid &g = s.g;
+    // decompose only when the solve is big enough to pay for its exchanges (sim.h, dist_min_unknowns); the size of the
+    // previous solve decides, so that every rank takes the same branch
+    const bool replicate = s.nranks > 1 && (long long)s.pres_last_unknowns < s.dist_min_unknowns * s.nranks;
+    const int mode = s.nranks > 1 ? (replicate ? 1 : 0) : -1;
+#ifndef FLIP_CPU_EMU
+    if (mode != s.pres_last_mode && s.cg_graph[0]) {
+        cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[0]);
+        s.cg_graph[0] = nullptr;
+    }
+#endif
+    s.pres_last_mode = mode;
+    ReplicatedGuard replicated(s, replicate);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
@@ -156,6 +168,7 @@ void solve_pressure(Sim &s, float dt) {
     s.pres_stats.iters = h.iter; s.pres_stats.converged = h.converged; s.pres_stats.resid = h.resid;
     s.pres_stats.bmax = h.bmax; s.pres_stats.skipped = (h.iter == 0 && h.converged) ? 1 : 0;
     s.pres_stats.blocks = s.count_host[0]; s.pres_stats.unknowns = s.count_host[1];
+    s.pres_last_unknowns = s.count_host[1];
     s.pres_stats.ms = ms;
     if (s.verbose) {
         printf("\tpressure: %d iterations, max|r| %.3e, %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,

@@ -821,13 +821,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     const Grid &g = s.g;
     // The multigrid hierarchy is not slab-decomposed yet: with several ranks every rank runs the whole
     // (deterministic, hence bit-identical) multigrid solve instead of a slab of the 50x slower Jacobi-PCG.
-    struct Replicated {
-        Sim &s; int nranks, bz0, bz1;
-        Replicated(Sim &sim, bool on) : s(sim), nranks(sim.nranks), bz0(sim.bz0), bz1(sim.bz1) {
-            if (on) { s.nranks = 1; s.bz0 = 0; s.bz1 = s.g.nbz; }
-        }
-        ~Replicated() { s.nranks = nranks; s.bz0 = bz0; s.bz1 = bz1; }
-    } replicated(s, s.visc_precond == 2 && s.nranks > 1);
+    ReplicatedGuard replicated(s, s.visc_precond == 2 && s.nranks > 1);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));

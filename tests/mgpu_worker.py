@@ -1,6 +1,8 @@
 """Worker for the multi-GPU parity test: launched with torchrun, one rank per GPU.
-Every rank steps the same scene with the k-slab-decomposed solves; rank 0 also steps a
-single-GPU simulation and compares."""
+  mgpu_worker.py N decomposed   every solve k-slab decomposed (diagonal-preconditioned CG, exchanges every iteration)
+  mgpu_worker.py N default      the shipping policy: multigrid viscosity solve replicated, pressure solve decomposed
+                                only above dist_min_unknowns per rank
+Rank 0 also steps a single-GPU simulation and compares."""
 import os
 import sys
 
@@ -19,9 +21,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    mode = sys.argv[2] if len(sys.argv) > 2 else "default"
     phi, p = _analytic_scene(n)
     sim = FlipSim(n, n, n, 1.0 / n)
     sim.set_solid_sdf(phi); sim.set_particles(p); sim.set_viscosity(2.0)
+    if mode == "decomposed":
+        sim.set_param("dist_min_unknowns", 0)
+        sim.set_param("viscosity_precond", 0)
     box = [sim.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     sim.dist_init(rank, world, box[0])
@@ -43,12 +49,14 @@ def main():
     if rank == 0:
         single = FlipSim(n, n, n, 1.0 / n)
         single.set_solid_sdf(phi); single.set_particles(p); single.set_viscosity(2.0)
+        if mode == "decomposed":
+            single.set_param("viscosity_precond", 0)
         for _ in range(3):
             single.advance(0.01)
         b = single.get_particles()
         st1 = single.stats()
         err = float(np.abs(out[:, :3] - b[:, :3]).max())
-        print("MGPU_RESULT world=%d replicas_identical=%d max_pos_diff_vs_single=%.3e visc_it=%d/%d pres_it=%d/%d unknowns=%d/%d"
+        print("MGPU_RESULT mode=" + mode + " world=%d replicas_identical=%d max_pos_diff_vs_single=%.3e visc_it=%d/%d pres_it=%d/%d unknowns=%d/%d"
               % (world, int(ok.item()), err, st["viscosity_iterations"], st1["viscosity_iterations"], st["pressure_iterations"],
                  st1["pressure_iterations"], st["viscosity_unknowns"], st1["viscosity_unknowns"]), flush=True)
         assert ok.item() == 1

@@ -68,12 +68,14 @@ def test_slab_bounds_cover_all_block_layers():
 
 
 @pytest.mark.gpu
-def test_two_gpu_slab_solves_match_single_gpu():
+@pytest.mark.parametrize("mode", ["decomposed", "default"])
+def test_two_gpu_solves_match_single_gpu(mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29733", os.path.join(ROOT, "tests", "mgpu_worker.py"), "64"],
+                        "127.0.0.1", "--master-port", "29733" if mode == "default" else "29735",
+                        os.path.join(ROOT, "tests", "mgpu_worker.py"), "64", mode],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_RESULT" in r.stdout
