@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Gri
     const int task = blockIdx.x * GMG_BUILD_WARPS + wid;        // (row, mp), mp fastest
     if (task >= 3 * nrows_c) return;                            // whole warp leaves together; no block-wide barrier below
     const int r = task / 3, mp = task - 3 * r;
+    // A_c is symmetric: the blocks below the diagonal (row component > column component) are mirrored from the ones
+    // above it by k_gmg_mirror instead of being computed a second time (a third of the tasks)
+    if (rows_c[r] / gc.total > mp) return;
     double *acc = acc_s[wid];
     float *wP = wP_s[wid];
     int *sslot = sslot_s[wid];
@@ -347,6 +350,31 @@ __global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Gri
     }
     __syncwarp();
     for (int q = lane; q < W.size; q += 32) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q]);
+}
+
+// lower blocks of the symmetric A_c: entry (row (m; J), column (mp; J + e)) with mp < m is entry
+// (row (mp; J + e), column (m; J)) of an upper block; the windows of (m, mp) and (mp, m) are mirror images.
+// One thread per (row, slot of a lower block).
+__global__ void __launch_bounds__(256) k_gmg_mirror(Grid g, const int *__restrict__ rows, int nrows, const int *__restrict__ rowmap,
+                                                     float *__restrict__ S) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = (int)(t / 160), q = (int)(t - (long long)r * 160);
+    if (r >= nrows) return;
+    const int enc = rows[r];
+    const int m = enc / g.total, id = enc - m * g.total;
+    if (m == 0) return;                       // rows of component 0 have no lower block
+    const int mp = q / 80, ql = q - mp * 80;  // lower blocks: column components 0 .. m-1, 80 slots each
+    if (mp >= m) return;
+    const GWin W = gmg_window(m, mp);
+    const int ei = W.lo[0] + ql % W.n[0], ej = W.lo[1] + (ql / W.n[0]) % W.n[1], ek = W.lo[2] + ql / (W.n[0] * W.n[1]);
+    float v = 0.0f;
+    const int ro = rowmap[mp * g.total + id + ei + ej * SY(g) + ek * SZ(g)];
+    if (ro >= 0) {
+        const GWin U = gmg_window(mp, m);     // the upper block's window holds the offset -e
+        const int slot = U.base + ((-ek - U.lo[2]) * U.n[1] + (-ej - U.lo[1])) * U.n[0] + (-ei - U.lo[0]);
+        v = S[(size_t)ro * GMG_STRIDE + slot];
+    }
+    S[(size_t)r * GMG_STRIDE + W.base + ql] = v;
 }
 
 // dense diagonal of an explicit level (also its unknown flag) = the (0,0,0) slot of the (m,m) window, and the

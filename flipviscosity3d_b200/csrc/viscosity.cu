@@ -615,6 +615,8 @@ static void gmg_build(Sim &s, GMG &M) {
                         (const float *)F.diag, (const float *)F.pn, (const float *)nullptr, (const int *)F.rowmap,
                         (const float *)F.S, F.nrows);
         }
+        FLIP_LAUNCH(k_gmg_mirror, cdiv(160LL * L.nrows, 256), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const int *)L.rowmap, L.S);
+        s.kernel_launches++;
         FLIP_LAUNCH_SYNC(k_gmg_diag, cdiv(L.nrows, 8), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const float *)L.S, L.diag, L.wj, M.omega);
         s.kernel_launches += 3;
         M.nlevels = l + 1;
