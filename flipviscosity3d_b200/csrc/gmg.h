@@ -17,10 +17,11 @@
 //                 (S[row * 240 + slot]); one WARP applies one row (coalesced 960-byte read, 8 slots
 //                 per lane, shuffle reduction), so even the 100-row levels finish in one memory
 //                 round trip.  Vectors stay in the dense padded layout: neighbours are plain offsets.
-//   set-up        one thread per (coarse row, column component) accumulates its <= 80 slots in
-//                 shared memory in a fixed order: no atomics, bit-reproducible.
-//   cycle         V(2,2), damped Jacobi, fp32 inside (the outer CG stays fp64), symmetric, so
-//                 plain CG remains valid.
+//   set-up        one warp per (coarse row, column component) accumulates its <= 80 slots in fp64 in shared
+//                 memory in a fixed order (no atomics, bit-reproducible); blocks below the diagonal are mirrored.
+//   cycle         V-cycle with 3 / 1 / 2 damped-Jacobi sweeps before = after the coarse correction on level 0 /
+//                 level 1 / deeper levels, exact dense solve on the last level (<= 128 rows), fp32 inside (the outer
+//                 CG stays fp64), symmetric, so plain CG remains valid.
 #pragma once
 #include "vmg.h"
 

@@ -539,11 +539,6 @@ static GLevelDev gmg_dev(const GLevel &L) {
     d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
     return d;
 }
-static VLevelDev gmg_vdev(const GLevel &L, const float *coef) {
-    VLevelDev d;
-    d.g = L.g; d.coef = coef; d.diag = L.diag; d.blk_list = L.blk_list; d.blk_count = L.blk_count;
-    return d;
-}
 static int gmg_grid(const Sim &s, const GLevel &L) {
     int G = cg_grid(s);
     return L.g.nblocks < G ? L.g.nblocks : G;
