@@ -189,10 +189,23 @@ def run_b200(args):
         dist.broadcast_object_list(box, src=0)
         sim.dist_init(rank, world, box[0])
         if not args.no_p2p:
-            # per-iteration reductions / halos through peer memory (CUDA IPC) instead of NCCL
-            blobs = [None] * world
-            dist.all_gather_object(blobs, sim.dist_p2p_export())
-            sim.dist_p2p_import(blobs)
+            # per-iteration reductions / halos through peer memory (CUDA IPC) instead of NCCL; if any rank cannot map
+            # its peers (no P2P path between two devices) every rank stays on NCCL
+            ok = 1
+            try:
+                blobs = [None] * world
+                dist.all_gather_object(blobs, sim.dist_p2p_export())
+                sim.dist_p2p_import(blobs)
+            except Exception as e:
+                ok = 0
+                print("bench.py: rank %d: peer-memory exchange unavailable (%s)" % (rank, e), file=sys.stderr)
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    print("bench.py: rank %d: falling back to NCCL exchanges because another rank could not map its peers" % rank, file=sys.stderr)
+                args.no_p2p = True
+                sim.set_param("dist_p2p", 0)
 
     def barrier_sync():
         if world > 1:

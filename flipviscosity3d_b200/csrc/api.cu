@@ -551,6 +551,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_flexible") s.mg_flexible = (int)value;
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
     else if (n == "dist_min_unknowns") s.dist_min_unknowns = (long long)value;
+    else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // back to NCCL for the per-iteration exchanges
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;
