@@ -63,6 +63,8 @@ SYMBOLS = {
     "flip_set_param": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "flip_get_stats": (C.c_int, [_H, C.POINTER(flip_stats)]),
     "flip_time_kernel": (C.c_int, [_H, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+    "flip_event_record": (C.c_int, [_H, C.c_int]),
+    "flip_event_elapsed_ms": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "flip_dist_unique_id": (C.c_int, [C.c_void_p]),
     "flip_dist_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "flip_dist_p2p_blob_size": (C.c_int, []),

@@ -111,6 +111,7 @@ void sim_free(Sim &s) {
     // graphs may hold captured NCCL kernels: destroy them before the communicator
     for (int q = 0; q < 2; q++) if (s.cg_graph[q]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[q]); s.cg_graph[q] = 0; }
 #endif
+    for (int q = 0; q < 4; q++) if (s.user_ev[q]) { cudaEventDestroy((cudaEvent_t)s.user_ev[q]); s.user_ev[q] = 0; }
     try { dist_shutdown(s); } catch (...) {}
     viscosity_free(s);
     free_particles(s);
@@ -599,6 +600,23 @@ int flip_time_kernel(flip_sim *h, const char *name, int reps, float *ms_per_laun
         if (rc != 0) return fail_inval(s, rc == -2 ? "flip_time_kernel: unknown kernel name" : "flip_time_kernel: no viscosity solve to time yet");
     } catch (const std::exception &e) { s.last_error = e.what(); return FLIP_ECUDA; }
     return FLIP_OK;
+}
+
+int flip_event_record(flip_sim *h, int slot) {
+    API_BEGIN(h)
+    if (slot < 0 || slot >= 4) return fail_inval(s, "flip_event_record: slot must be 0..3");
+    if (!s.user_ev[slot]) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); s.user_ev[slot] = (void *)e; }
+    CUDA_CHECK(cudaEventRecord((cudaEvent_t)s.user_ev[slot], s.stream));
+    API_END()
+}
+
+int flip_event_elapsed_ms(flip_sim *h, int slot_from, int slot_to, float *ms) {
+    API_BEGIN(h)
+    if (!ms || slot_from < 0 || slot_from >= 4 || slot_to < 0 || slot_to >= 4 || !s.user_ev[slot_from] || !s.user_ev[slot_to])
+        return fail_inval(s, "flip_event_elapsed_ms: bad slots (record both first)");
+    CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)s.user_ev[slot_to]));
+    CUDA_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t)s.user_ev[slot_from], (cudaEvent_t)s.user_ev[slot_to]));
+    API_END()
 }
 
 int flip_dist_unique_id(void *out128) {

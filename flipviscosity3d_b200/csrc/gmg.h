@@ -2,14 +2,14 @@
 //
 // The reference preconditions with MIC(0) (src/pcgsolver/pcgsolver.h:62-214), a sequential
 // recurrence that barely beats the diagonal on this coupled system (64^3: 364 vs 468 iterations)
-// and hits its 700-iteration cap from 128^3 up.  The rediscretised V-cycle of vmg.h
+// and hits its 700-iteration cap from 128^3 up.  A rediscretised V-cycle (round 1, removed)
 // gains 5-13x; its weak point, measured on a scipy prototype of the same operator
 // (dev/visc_proto.py), is the coarse operator next to the free surface.  Here the coarse operators
-// are the exact Galerkin products  A_c = P^T A P / 8  with the staggered trilinear transfers of
-// vmg.h (linear along the face normal, cell-centred linear across it, renormalised at the free
+// are the exact Galerkin products  A_c = P^T A P / 8  with staggered trilinear
+// transfers (linear along the face normal, cell-centred linear across it, renormalised at the free
 // surface): 20-25x fewer iterations than the diagonal at 64^3-128^3, and nothing to tune.
 //
-//   level 0       the solver's own matrix-free coupled stencil (k_visc_apply / vmg_row)
+//   level 0       the solver's own matrix-free coupled stencil (k_visc_apply)
 //   levels >= 1   explicit windowed stencils.  A product of trilinear transfers with a 15-point
 //                 operator closes on a fixed window per (row component m, column component m'):
 //                 m == m': 3 x 5 x 5 (3 along the face normal), m != m': 4 x 4 x 5  ->  235 slots
@@ -23,11 +23,47 @@
 //                 level 1 / deeper levels, exact dense solve on the last level (<= 128 rows), fp32 inside (the outer
 //                 CG stays fp64), symmetric, so plain CG remains valid.
 #pragma once
-#include "vmg.h"
+#include "cg.h"
 
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
+
+// one axis of the prolongation: fine index n -> up to two coarse indices and weights
+FLIP_D void gmg_parents(bool own, int n, int &p0, int &p1, float &w0, float &w1) {
+    if (own) {
+        p0 = n >> 1;
+        if ((n & 1) == 0) { p1 = p0; w0 = 1.0f; w1 = 0.0f; }
+        else { p1 = p0 + 1; w0 = 0.5f; w1 = 0.5f; }
+    } else {
+        p0 = n >> 1;
+        p1 = (n & 1) ? p0 + 1 : p0 - 1;
+        w0 = 0.75f; w1 = 0.25f;
+    }
+}
+
+// sum of the interpolation weights of a fine face's coarse parents that are unknowns.  The
+// interpolation is renormalised by it, so that faces next to the free surface (whose outer parents
+// carry no equation) are extrapolated from the liquid side instead of being pulled towards 0.
+FLIP_D float gmg_pnorm(int m, int i, int j, int k, const Grid &gc, const float *__restrict__ diag_c) {
+    int pi[2], pj[2], pk[2];
+    float wi[2], wj[2], wk[2];
+    gmg_parents(m == 0, i, pi[0], pi[1], wi[0], wi[1]);
+    gmg_parents(m == 1, j, pj[0], pj[1], wj[0], wj[1]);
+    gmg_parents(m == 2, k, pk[0], pk[1], wk[0], wk[1]);
+    const float *d = diag_c + (size_t)m * gc.total;
+    float sum = 0.0f;
+    for (int c2 = 0; c2 < 2; c2++)
+        for (int b2 = 0; b2 < 2; b2++)
+            for (int a = 0; a < 2; a++) {
+                float w = wi[a] * wj[b2] * wk[c2];
+                if (w == 0.0f) continue;
+                int I = pi[a], J = pj[b2], K = pk[c2];
+                if (I < 0 || J < 0 || K < 0 || I > gc.ni || J > gc.nj || K > gc.nk) continue;
+                if (d[gidx(gc, I, J, K)] != 0.0f) sum += w;
+            }
+    return sum;
+}
 
 struct GWin { int lo[3], n[3], base, size; };
 
@@ -179,7 +215,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_pnorm(Grid g, const int *__r
         if (!c.inside) continue;
         int id = gidx(g, c.i, c.j, c.k);
         for (int m = 0; m < 3; m++)
-            pn[m * T + id] = diag[m * T + id] != 0.0f ? vmg_pnorm(m, c.i, c.j, c.k, gc, diag_c) : 0.0f;
+            pn[m * T + id] = diag[m * T + id] != 0.0f ? gmg_pnorm(m, c.i, c.j, c.k, gc, diag_c) : 0.0f;
     }
 }
 
@@ -320,9 +356,9 @@ __global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Gri
         // ---- this lane's <= 8 contributions (slot, value); slot -1 = none
         int pi[2], pj[2], pk[2];
         float wi[2], wj[2], wk[2];
-        vmg_parents(mp == 0, ji, pi[0], pi[1], wi[0], wi[1]);
-        vmg_parents(mp == 1, jj, pj[0], pj[1], wj[0], wj[1]);
-        vmg_parents(mp == 2, jk, pk[0], pk[1], wk[0], wk[1]);
+        gmg_parents(mp == 0, ji, pi[0], pi[1], wi[0], wi[1]);
+        gmg_parents(mp == 1, jj, pj[0], pj[1], wj[0], wj[1]);
+        gmg_parents(mp == 2, jk, pk[0], pk[1], wk[0], wk[1]);
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             int a = q & 1, b2 = (q >> 1) & 1, c2 = q >> 2;
@@ -539,9 +575,9 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
 FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float *__restrict__ xc) {
     int pi[2], pj[2], pk[2];
     float wi[2], wj[2], wk[2];
-    vmg_parents(m == 0, i, pi[0], pi[1], wi[0], wi[1]);
-    vmg_parents(m == 1, j, pj[0], pj[1], wj[0], wj[1]);
-    vmg_parents(m == 2, k, pk[0], pk[1], wk[0], wk[1]);
+    gmg_parents(m == 0, i, pi[0], pi[1], wi[0], wi[1]);
+    gmg_parents(m == 1, j, pj[0], pj[1], wj[0], wj[1]);
+    gmg_parents(m == 2, k, pk[0], pk[1], wk[0], wk[1]);
     const float *x = xc + (size_t)m * gc.total;
     float v = 0.0f;
     for (int c2 = 0; c2 < 2; c2++)

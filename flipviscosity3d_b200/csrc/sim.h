@@ -45,7 +45,7 @@ struct Sim {
     int visc_maxit = 700;               // src/viscositysolver.h:202
     int visc_maxit_scale = 40;
     int visc_warm_start = 0;            // start the viscosity CG from the current velocity instead of 0
-    int visc_precond = 2;               // 2 = Galerkin multigrid (gmg.h, default), 0 = diagonal, 1 = rediscretised multigrid (vmg.h)
+    int visc_precond = 2;               // 2 = Galerkin multigrid (gmg.h, default), 0 = diagonal
     int mg_sweeps = 2;                  // damped-Jacobi sweeps before = after the coarse correction
     int mg_coarse_sweeps = 24;
     float mg_omega = 0.5f;
@@ -106,7 +106,6 @@ struct Sim {
     double *cg_x = 0, *cg_r = 0, *cg_s = 0, *cg_q = 0;   // [3*total] (pressure uses component 0)
     double *cg_z = 0;         // [3*total] preconditioned residual (multigrid mode; u = M^-1 r in the single-reduction CG)
     double *cg_w = 0;         // [3*total] w = A u (single-reduction CG)
-    void *vmg = 0;            // viscosity multigrid hierarchy (VMG*, viscosity.cu)
     void *gmg = 0;            // Galerkin multigrid hierarchy (GMG*, gmg.h / viscosity.cu)
     float *vvol = 0;          // 7 volume grids [7*total]: center,U,V,W,edgeU,edgeV,edgeW
     float *vnode = 0;         // 7 nodal phi grids [7*total]
@@ -136,6 +135,8 @@ struct Sim {
     long long dist_min_unknowns = 1000000;
     int pres_last_unknowns = 0;   // of the previous pressure solve (identical on every rank)
     int pres_last_mode = -1;      // 0 decomposed, 1 replicated: a flip invalidates the captured CG graph
+
+    void *user_ev[4] = {0, 0, 0, 0};   // cudaEvent_t slots of flip_event_record (device-side timing for callers)
 
     // stats of the last substep
     SolveStats pres_stats = {0, 0, 0, 0, 0, 0, 0, 0};

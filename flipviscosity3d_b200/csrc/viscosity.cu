@@ -318,158 +318,14 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
 }
 
 
-// ------------------------------------------------------------------------------------------
-// multigrid hierarchy (vmg.h): allocation, per-solve coarsening, V-cycle launcher
-// ------------------------------------------------------------------------------------------
 template <class T>
 static void vmg_dev_alloc(T *&p, size_t n) {
     CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
     CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
 }
 
-static VMG *vmg_get(Sim &s) {
-    if (s.vmg) return (VMG *)s.vmg;
-    VMG *M = new VMG();
-    s.vmg = M;
-    Grid g = s.g;
-    for (int l = 0; l < VMG_MAX_LEVELS; l++) {
-        VLevel &L = M->lv[l];
-        L.g = g;
-        size_t T = (size_t)g.total;
-        vmg_dev_alloc(L.x[0], 3 * T);
-        vmg_dev_alloc(L.x[1], 3 * T);
-        vmg_dev_alloc(L.r, 3 * T);
-        if (l == 0) {
-            L.coef = s.vcoef; L.diag = s.vdiag; L.vol = s.vvol + T; L.b = nullptr; L.wall = s.fstate;
-            L.blk_flag = s.blk_flag; L.blk_list = s.blk_list; L.blk_count = s.blk_count;
-            L.owns = false;
-        } else {
-            vmg_dev_alloc(L.coef, 4 * T); vmg_dev_alloc(L.diag, 3 * T); vmg_dev_alloc(L.vol, 3 * T);
-            vmg_dev_alloc(L.b, 3 * T);
-            vmg_dev_alloc(L.wall, 3 * T);
-            vmg_dev_alloc(L.blk_flag, (size_t)g.nblocks); vmg_dev_alloc(L.blk_list, (size_t)g.nblocks);
-            vmg_dev_alloc(L.blk_count, 1);
-            L.owns = true;
-        }
-        M->nlevels = l + 1;
-        int mn = g.ni < g.nj ? g.ni : g.nj;
-        mn = mn < g.nk ? mn : g.nk;
-        if (mn <= 4) break;
-        g = make_grid((g.ni + 1) / 2, (g.nj + 1) / 2, (g.nk + 1) / 2, g.dx * 2.0f);
-    }
-    M->nalloc = M->nlevels;
-    M->allocated = true;
-    return M;
-}
-
 static void gmg_free(Sim &s);
-void viscosity_free(Sim &s) {
-    gmg_free(s);
-    VMG *M = (VMG *)s.vmg;
-    if (!M) return;
-    for (int l = 0; l < M->nalloc; l++) {
-        VLevel &L = M->lv[l];
-        cudaFree(L.x[0]); cudaFree(L.x[1]); cudaFree(L.r);
-        if (L.owns) {
-            cudaFree(L.coef); cudaFree(L.diag); cudaFree(L.vol); cudaFree(L.b); cudaFree(L.wall);
-            cudaFree(L.blk_flag); cudaFree(L.blk_list); cudaFree(L.blk_count);
-        }
-    }
-    delete M;
-    s.vmg = nullptr;
-}
-
-static VLevelDev vmg_dev(const VLevel &L) {
-    VLevelDev d;
-    d.g = L.g; d.coef = L.coef; d.diag = L.diag; d.blk_list = L.blk_list; d.blk_count = L.blk_count;
-    return d;
-}
-
-static int vmg_grid(const Sim &s, const VLevel &L) {
-    int G = cg_grid(s);
-    return L.g.nblocks < G ? L.g.nblocks : G;
-}
-
-// coarse operators + block lists for this solve (level 0 is the solver's own fields)
-static void vmg_build(Sim &s, VMG &M) {
-    M.pre = s.mg_sweeps < 1 ? 1 : s.mg_sweeps;
-    M.coarse_sweeps = s.mg_coarse_sweeps;
-    M.omega = s.mg_omega;
-    M.alpha = s.mg_alpha;
-    M.nlevels = s.mg_levels < M.nalloc ? (s.mg_levels < 1 ? 1 : s.mg_levels) : M.nalloc;
-    for (int l = 0; l < M.nlevels; l++) {
-        VLevel &L = M.lv[l];
-        size_t T = (size_t)L.g.total;
-        // vectors are read with a one-cell halo: zero outside the unknowns of THIS solve
-        CUDA_CHECK(cudaMemsetAsync(L.x[0], 0, 3 * T * sizeof(float), s.stream));
-        CUDA_CHECK(cudaMemsetAsync(L.x[1], 0, 3 * T * sizeof(float), s.stream));
-        CUDA_CHECK(cudaMemsetAsync(L.r, 0, 3 * T * sizeof(float), s.stream));
-        if (l == 0) continue;
-        CUDA_CHECK(cudaMemsetAsync(L.b, 0, 3 * T * sizeof(float), s.stream));
-        const VLevel &F = M.lv[l - 1];
-        long long n = (long long)(L.g.ni + 1) * (L.g.nj + 1) * (L.g.nk + 1);
-        FLIP_LAUNCH(k_vmg_coarsen_coefs, cdiv(n, 256), 256, s.stream, L.g, F.g, (const float *)F.coef, (const float *)F.vol,
-                    (const float *)F.diag, L.coef, L.vol, L.diag, (const unsigned char *)F.wall, L.wall);
-        FLIP_LAUNCH(k_vmg_classify, cdiv(n, 256), 256, s.stream, L.g, (const float *)L.vol, L.diag, L.wall, s.mg_minvol);
-        if (s.mg_prune) FLIP_LAUNCH(k_vmg_prune, cdiv(n, 256), 256, s.stream, L.g, L.coef, (const float *)L.diag, (const unsigned char *)L.wall);
-        FLIP_LAUNCH(k_vmg_coarsen_rows, cdiv(n, 256), 256, s.stream, L.g, (const float *)L.coef, (const float *)L.vol, L.diag);
-        s.kernel_launches += 4;
-        DiagViscosity d{L.diag, L.g.total};
-        build_block_list_on<3>(s, L.g, d, L.blk_flag, L.blk_list, L.blk_count);
-    }
-    KERNEL_CHECK();
-}
-
-// z = Vcycle(r): r is the CG residual (fp64) on level 0
-static void vmg_vcycle(Sim &s, VMG &M, const double *r_in, double *z_out, const CGState *st) {
-    const float w = M.omega;
-    int cur[VMG_MAX_LEVELS];
-    auto first_d = &k_vmg_first<double>; auto smooth_d = &k_vmg_smooth<double>; auto resid_d = &k_vmg_residual<double>;
-    auto first_f = &k_vmg_first<float>; auto smooth_f = &k_vmg_smooth<float>; auto resid_f = &k_vmg_residual<float>;
-    int last = M.nlevels - 1;
-    // downstroke
-    for (int l = 0; l <= last; l++) {
-        VLevel &L = M.lv[l];
-        VLevelDev D = vmg_dev(L);
-        int G = vmg_grid(s, L);
-        if (l > 0) {
-            VLevelDev Dc = D;
-            FLIP_LAUNCH(k_vmg_restrict, G, CG_THREADS, s.stream, Dc, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, st);
-            s.kernel_launches++;
-        }
-        int sweeps = (l == last && last > 0) ? 1 + M.coarse_sweeps : M.pre;
-        cur[l] = 0;
-        if (l == 0) FLIP_LAUNCH(first_d, G, CG_THREADS, s.stream, D, r_in, L.x[0], w, st);
-        else FLIP_LAUNCH(first_f, G, CG_THREADS, s.stream, D, (const float *)L.b, L.x[0], w, st);
-        for (int k = 1; k < sweeps; k++) {
-            if (l == 0) FLIP_LAUNCH(smooth_d, G, CG_THREADS, s.stream, D, r_in, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], w, st);
-            else FLIP_LAUNCH(smooth_f, G, CG_THREADS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], w, st);
-            cur[l] ^= 1;
-        }
-        s.kernel_launches += sweeps;
-        if (l < last) {
-            if (l == 0) FLIP_LAUNCH(resid_d, G, CG_THREADS, s.stream, D, r_in, (const float *)L.x[cur[l]], L.r, M.lv[l + 1].g, (const float *)M.lv[l + 1].diag, st);
-            else FLIP_LAUNCH(resid_f, G, CG_THREADS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, M.lv[l + 1].g, (const float *)M.lv[l + 1].diag, st);
-            s.kernel_launches++;
-        }
-    }
-    // upstroke
-    for (int l = last - 1; l >= 0; l--) {
-        VLevel &L = M.lv[l];
-        VLevelDev D = vmg_dev(L);
-        int G = vmg_grid(s, L);
-        FLIP_LAUNCH(k_vmg_prolong, G, CG_THREADS, s.stream, D, M.lv[l + 1].g, (const float *)M.lv[l + 1].diag, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], M.alpha, st);
-        for (int k = 0; k < M.pre; k++) {
-            if (l == 0) FLIP_LAUNCH(smooth_d, G, CG_THREADS, s.stream, D, r_in, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], w, st);
-            else FLIP_LAUNCH(smooth_f, G, CG_THREADS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], w, st);
-            cur[l] ^= 1;
-        }
-        s.kernel_launches += 1 + M.pre;
-    }
-    VLevelDev D0 = vmg_dev(M.lv[0]);
-    FLIP_LAUNCH(k_vmg_export, vmg_grid(s, M.lv[0]), CG_THREADS, s.stream, D0, (const float *)M.lv[0].x[cur[0]], z_out, st);
-    s.kernel_launches++;
-}
+void viscosity_free(Sim &s) { gmg_free(s); }
 
 // ------------------------------------------------------------------------------------------
 // Galerkin multigrid hierarchy (gmg.h): allocation, per-solve set-up, V-cycle launcher
@@ -851,13 +707,6 @@ void stage_apply_viscosity(Sim &s, float dt) {
         h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit,
                        [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); },
                        s.visc_warm_start ? (const float *)s.vel : nullptr);
-    } else if (s.visc_precond == 1 && s.nranks == 1) {
-        VMG *M = vmg_get(s);
-        vmg_build(s, *M);
-        P.z = s.cg_z;
-        h = run_cg_mg<3>(s, P, diag, 0.0, s.visc_tol, maxit,
-                         [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); },
-                         [&](const CGState *cst) { vmg_vcycle(s, *M, (const double *)P.r, P.z, cst); });
     } else if (s.cg_variant_viscosity == 1) {
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
         CGParams Pu = P;
@@ -893,46 +742,6 @@ void stage_apply_viscosity(Sim &s, float dt) {
         printf("\tviscosity: %d iterations, max|r| %.3e (tol %.3e), %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,
                h.tol, accept ? (h.converged ? "converged" : "accepted") : "FAILED", *s.count_host, ms);
     }
-}
-
-// ---- debug access to the multigrid hierarchy (tests only) ------------------------------------
-extern "C" int flip_debug_vmg_info(void *hsim, int level, int *out /*[8]: ni,nj,nk,ax,ay,az,total,nlevels*/) {
-    Sim &s = *(Sim *)hsim;  // flip_sim's first member is the Sim
-    VMG *M = (VMG *)s.vmg;
-    if (!M || level < 0 || level >= M->nalloc) return -1;
-    const Grid &g = M->lv[level].g;
-    out[0] = g.ni; out[1] = g.nj; out[2] = g.nk; out[3] = g.ax; out[4] = g.ay; out[5] = g.az; out[6] = g.total; out[7] = M->nalloc;
-    return 0;
-}
-// which: 0 coef(4T) 1 diag(3T) 2 vol(3T) 3 x0(3T) 4 x1(3T) 5 b(3T) 6 r(3T); raw padded layout
-extern "C" int flip_debug_vmg_field(void *hsim, int level, int which, float *out) {
-    Sim &s = *(Sim *)hsim;
-    VMG *M = (VMG *)s.vmg;
-    if (!M || level < 0 || level >= M->nalloc) return -1;
-    VLevel &L = M->lv[level];
-    size_t T = (size_t)L.g.total;
-    const float *src = which == 0 ? L.coef : which == 1 ? L.diag : which == 2 ? L.vol : which == 3 ? L.x[0] : which == 4 ? L.x[1]
-                       : which == 5 ? L.b : L.r;
-    size_t n = (which == 0 ? 4 : 3) * T;
-    if (!src) return -2;
-    cudaStreamSynchronize(s.stream);
-    return cudaMemcpy(out, src, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
-}
-
-// z = Vcycle(r) on raw padded fp64 arrays [3*total] using the hierarchy of the last solve (tests only)
-extern "C" int flip_debug_vmg_apply(void *hsim, const double *r_host, double *z_host) {
-    Sim &s = *(Sim *)hsim;
-    VMG *M = (VMG *)s.vmg;
-    if (!M) return -1;
-    size_t n = 3 * (size_t)s.g.total;
-    try {
-        CUDA_CHECK(cudaMemcpy(s.cg_q, r_host, n * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, n * sizeof(double), s.stream));
-        vmg_vcycle(s, *M, (const double *)s.cg_q, s.cg_z, nullptr);
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        CUDA_CHECK(cudaMemcpy(z_host, s.cg_z, n * sizeof(double), cudaMemcpyDeviceToHost));
-    } catch (...) { return -2; }
-    return 0;
 }
 
 // y = A x for the viscosity system of the last solve, on raw padded fp64 arrays [3*total] (tests /

@@ -225,6 +225,14 @@ class FlipSim:
         self._ck(self.lib.flip_time_kernel(self.h, name.encode(), int(reps), C.byref(ms), C.byref(nb)))
         return float(ms.value), int(nb.value)
 
+    def event_record(self, slot):
+        self._ck(self.lib.flip_event_record(self.h, int(slot)))
+
+    def event_elapsed_ms(self, slot_from, slot_to):
+        ms = C.c_float()
+        self._ck(self.lib.flip_event_elapsed_ms(self.h, int(slot_from), int(slot_to), C.byref(ms)))
+        return float(ms.value)
+
     def stats(self):
         st = _lib.flip_stats()
         self._ck(self.lib.flip_get_stats(self.h, C.byref(st)))

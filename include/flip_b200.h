@@ -132,7 +132,7 @@ int flip_set_valid(flip_sim *h, int comp, const uint8_t *in);
 /* ---- parameters and diagnostics ----
  * names: "pressure_tol" "pressure_maxit" "viscosity_tol" "viscosity_maxit" "viscosity_accept"
  *        "maxit_scale" "cg_chunk" "pic_ratio" "cfl" "verbose"   (defaults = the reference's)
- *        "viscosity_precond" 2 = Galerkin multigrid (default), 0 = diagonal, 1 = rediscretised multigrid;
+ *        "viscosity_precond" 2 = Galerkin multigrid (default), 0 = diagonal;
  *        "mg_sweeps" "mg_coarse_sweeps" "mg_omega" "mg_levels" "mg_chunk" "mg_flexible" tune the V-cycle */
 int flip_set_param(flip_sim *h, const char *name, double value);
 int flip_get_stats(flip_sim *h, flip_stats *out);
@@ -141,6 +141,12 @@ int flip_get_stats(flip_sim *h, flip_stats *out);
  * one launch moves.  names: "gmg_sweep_l1" (Jacobi sweep on the first explicit multigrid level), "visc_apply"
  * (matrix-free coupled-face stencil apply of the CG). */
 int flip_time_kernel(flip_sim *h, const char *name, int reps, float *ms_per_launch, uint64_t *algorithmic_bytes);
+
+/* Device-side timing for callers (no reference counterpart): records a CUDA event on the library's stream into one of
+ * four slots; flip_event_elapsed_ms waits for `slot_to` and returns the device time between the two records.  bench.py
+ * brackets its timed region with these (torch.cuda.Event only sees torch's own stream). */
+int flip_event_record(flip_sim *h, int slot);
+int flip_event_elapsed_ms(flip_sim *h, int slot_from, int slot_to, float *ms);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-threaded) ----
  * One process per GPU.  Rank 0 calls flip_dist_unique_id and ships the 128 bytes to the other

@@ -344,6 +344,59 @@ int ref_stage_apply_viscosity_ex(void *h, float dt, double tol, int maxit) {
     return 1;
 }
 
+/* Residual of a CANDIDATE solution in the reference's own assembled viscosity system: builds the system exactly as
+ * ViscositySolver::applyViscosityToVelocityField does (src/viscositysolver.cpp:41-63, 374-664) from the current
+ * pre-viscosity state, reads x from the candidate MAC fields through the reference's index table
+ * (src/viscositysolver.cpp:692-727 in reverse) and evaluates r = b - A x with the reference's CSR multiply
+ * (src/pcgsolver/sparsematrix.h:166-176).  out = {max|r|, max|b|, unknowns, max|x|, rows with a non-positive diagonal,
+ * max|r| over rows whose face control volume is > 0}.  The state of the simulation is not changed. */
+int ref_viscosity_residual(void *h, float dt, const float *u, const float *v, const float *w, double *out) {
+    Ref *r = (Ref *)h; StdoutMute mute(r->quiet);
+    FluidSimulation &s = r->sim;
+    ViscositySolverParameters params;
+    params.cellwidth = s._dx;
+    params.deltaTime = dt;
+    params.velocityField = &s._MACVelocity;
+    params.liquidSDF = &s._liquidSDF;
+    params.solidSDF = &s._solidSDF;
+    params.viscosity = &s._viscosity;
+    ViscositySolver vs;
+    vs._initialize(params);
+    vs._computeFaceStateGrid();
+    vs._computeVolumeGrid();
+    vs._computeMatrixIndexTable();
+    int n = vs._matrixIndex.matrixSize;
+    SparseMatrixd matrix(n);
+    std::vector<double> rhs(n, 0), x(n, 0), ax(n, 0), vol(n, 0);
+    vs._initializeLinearSystem(matrix, rhs);
+    int ni = r->ni, nj = r->nj, nk = r->nk;
+    for (int k = 0; k < nk; k++) for (int j = 0; j < nj; j++) for (int i = 0; i < ni + 1; i++) {
+        int m = vs._matrixIndex.U(i, j, k);
+        if (m != -1) { x[m] = u[i + (size_t)(ni + 1) * (j + (size_t)nj * k)]; vol[m] = vs._volumes.U(i, j, k); }
+    }
+    for (int k = 0; k < nk; k++) for (int j = 0; j < nj + 1; j++) for (int i = 0; i < ni; i++) {
+        int m = vs._matrixIndex.V(i, j, k);
+        if (m != -1) { x[m] = v[i + (size_t)ni * (j + (size_t)(nj + 1) * k)]; vol[m] = vs._volumes.V(i, j, k); }
+    }
+    for (int k = 0; k < nk + 1; k++) for (int j = 0; j < nj; j++) for (int i = 0; i < ni; i++) {
+        int m = vs._matrixIndex.W(i, j, k);
+        if (m != -1) { x[m] = w[i + (size_t)ni * (j + (size_t)nj * k)]; vol[m] = vs._volumes.W(i, j, k); }
+    }
+    vs._destroyVolumeGrid();
+    FixedSparseMatrix<double> fixed;
+    fixed.fromMatrix(matrix);
+    multiply(fixed, x, ax);
+    double rmax = 0, bmax = 0, xmax = 0, rmax_vol = 0; long long badDiag = 0;
+    for (int q = 0; q < n; q++) {
+        double res = std::fabs(rhs[q] - ax[q]);
+        rmax = std::max(rmax, res); bmax = std::max(bmax, std::fabs(rhs[q])); xmax = std::max(xmax, std::fabs(x[q]));
+        if (vol[q] > 0) rmax_vol = std::max(rmax_vol, res);
+        if (matrix(q, q) <= 0) badDiag++;
+    }
+    out[0] = rmax; out[1] = bmax; out[2] = (double)n; out[3] = xmax; out[4] = (double)badDiag; out[5] = rmax_vol;
+    return n;
+}
+
 void ref_stage_apply_viscosity(void *h, float dt) {
     Ref *r = (Ref *)h; StdoutMute mute(r->quiet);
     r->sim._applyViscosity(dt);
@@ -447,6 +500,14 @@ void ref_write_particles_ply(void *h, const char *path) {
     TriangleMesh m;
     for (size_t i = 0; i < r->sim.particles.size(); i++) m.vertices.push_back(r->sim.particles[i].position);
     m.writeMeshToPLY(path);
+}
+
+/* OBJ writer of the reference (src/trianglemesh.cpp:381-418) on the current particles */
+void ref_write_particles_obj(void *h, const char *path) {
+    Ref *r = (Ref *)h;
+    TriangleMesh m;
+    for (size_t i = 0; i < r->sim.particles.size(); i++) m.vertices.push_back(r->sim.particles[i].position);
+    m.writeMeshToOBJ(path);
 }
 
 /* reference PLY loader (src/trianglemesh.cpp:39-63); fails on files < 2048 B.

@@ -233,6 +233,15 @@ class RefSim:
         lib().ref_viscosity_diag(self.h, C.byref(it), C.byref(res), C.byref(ok), C.byref(unk))
         return dict(wrote=int(wrote), iters=it.value, resid=res.value, ok=ok.value, unknowns=unk.value)
 
+    def viscosity_residual(self, dt, u, v, w):
+        """max|b - A x| of candidate MAC fields in the reference's own assembled viscosity system (state unchanged)"""
+        u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32); w = np.ascontiguousarray(w, np.float32)
+        assert u.shape == self.shape_u() and v.shape == self.shape_v() and w.shape == self.shape_w()
+        out = (C.c_double * 6)()
+        lib().ref_viscosity_residual(self.h, C.c_float(dt), _fp(u), _fp(v), _fp(w), out)
+        return dict(resid=out[0], bmax=out[1], unknowns=int(out[2]), xmax=out[3], nonpositive_diagonals=int(out[4]),
+                    resid_faces_with_volume=out[5])
+
     def compute_weights(self):
         lib().ref_compute_weights(self.h)
 
@@ -264,3 +273,9 @@ class RefSim:
 
     def write_particles_ply(self, path):
         lib().ref_write_particles_ply(self.h, path.encode())
+
+    def write_particles_obj(self, path):
+        lib().ref_write_particles_obj(self.h, path.encode())
+
+    def reset_boundary(self):
+        lib().ref_reset_boundary(self.h)

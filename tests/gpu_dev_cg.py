@@ -7,7 +7,7 @@ from flipviscosity3d_b200 import FlipSim
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 phi, p = bench.build_scene(n)
 cases = [dict(use_graphs=0, cg_grid_mult=2), dict(use_graphs=1, cg_grid_mult=2), dict(use_graphs=1, cg_grid_mult=3), dict(use_graphs=1, cg_grid_mult=4),
-         dict(use_graphs=1, cg_grid_mult=4, cg_chunk=64), dict(viscosity_precond=1), dict(viscosity_precond=1, mg_sweeps=1)]
+         dict(use_graphs=1, cg_grid_mult=4, cg_chunk=64), ]
 for kw in cases:
     sim = FlipSim(n, n, n, 1.0 / n)
     sim.set_solid_sdf(phi); sim.set_particles(p); sim.set_viscosity(5.0)

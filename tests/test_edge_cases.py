@@ -102,3 +102,40 @@ def test_empty_particle_set_and_bad_arguments(lib):
         sim.get_field(99)
     with pytest.raises(FlipError):
         FlipSim(2, 16, 16, 1.0 / 16, lib=lib)        # grids smaller than 4 cells are rejected
+
+
+def test_viscosity_cap_accept_and_fail_branches(lib, oracle):
+    """ViscositySolver::_solveLinearSystem (src/viscositysolver.cpp:676-689): a solve that stops at its iteration
+    cap is still ACCEPTED when the residual is below the acceptable tolerance (10.0), otherwise it FAILS and
+    FluidSimulation::_applyViscosity ignores the result (src/fluidsimulation.cpp:194-195): the field stays untouched.
+    Same branches on the reference (raised / lowered through the harness) and on the library."""
+    sim, ref = pc.build_pair(lib, oracle, n=16, liquid="cube", boundary=None, viscosity=4.0)
+    pc.prepare_mid_substep(sim, ref)
+    pc.sync_grid_state(sim, ref)
+    before = [a.copy() for a in sim.get_mac()]
+    # (1) cap hit, residual < acceptable tolerance -> accepted, written back, not converged
+    sim.set_param("maxit_scale", 1)
+    sim.set_param("viscosity_maxit", 2)
+    sim.apply_viscosity(pc.DT)
+    st = sim.stats()
+    assert st["viscosity_iterations"] == 2 and st["viscosity_converged"] == 0 and st["viscosity_applied"] == 1
+    assert st["viscosity_residual"] < 10.0
+    assert any(not np.array_equal(a, b) for a, b in zip(sim.get_mac(), before))
+    info = ref.apply_viscosity(pc.DT, tol=1e-6, maxit=2)
+    assert info["iters"] == 2 and info["resid"] > 1e-6 * 0 and info["ok"] == 1 and info["wrote"] == 1   # same branch: accepted at the cap
+    # (2) cap hit, residual above the acceptable tolerance -> FAILED, field untouched
+    pc.sync_grid_state(sim, ref)   # the reference wrote its truncated iterate: reload the common pre-solve state
+    before = [a.copy() for a in sim.get_mac()]
+    sim.set_param("viscosity_accept", 1e-30)
+    sim.apply_viscosity(pc.DT)
+    st = sim.stats()
+    assert st["viscosity_iterations"] == 2 and st["viscosity_converged"] == 0 and st["viscosity_applied"] == 0
+    for a, b in zip(sim.get_mac(), before):
+        assert np.array_equal(a, b)
+    # (3) zero right-hand side (fluid at rest, no solid motion): success with 0 iterations (pcgsolver.h:254-258)
+    sim.set_param("viscosity_accept", 10.0); sim.set_param("viscosity_maxit", 700); sim.set_param("maxit_scale", 40)
+    zero = [np.zeros_like(a) for a in before]
+    sim.set_mac(*zero)
+    sim.apply_viscosity(pc.DT)
+    st = sim.stats()
+    assert st["viscosity_iterations"] == 0 and st["viscosity_converged"] == 1 and st["viscosity_applied"] == 1
