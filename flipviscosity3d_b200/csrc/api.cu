@@ -15,11 +15,9 @@ static std::string g_create_error;
 #define FLIP_BUILD_KIND "sm_100a"
 #endif
 
+// every device buffer comes from the handle's symmetric heap (heap.h), zero filled
 template <class T>
-static void dev_alloc(T *&p, size_t n) {
-    CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
-    CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
-}
+static void dev_alloc(Sim &s, T *&p, size_t n) { heap_alloc(s, p, n); }
 
 void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     s.g = make_grid(ni, nj, nk, dx);
@@ -31,65 +29,72 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     s.num_sms = prop.multiProcessorCount;
     CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    // Heap sizing: the fixed fields below take ~330 B per padded cell, the multigrid vectors ~70 B more; particles and
+    // the explicit multigrid rows come on top.  Later needs grow the heap by further chunks (until the peers map it).
+    s.heap.first_chunk = (size_t)520 * T + ((size_t)64 << 20);
+    s.heap.grow_chunk = (size_t)130 * T + ((size_t)64 << 20);
     // _particleRadius = (float)(_dx * 1.01*sqrt(3.0)/2.0)  (src/fluidsimulation.cpp:36)
     s.particle_radius = (float)((double)dx * 1.01 * sqrt(3.0) / 2.0);
     s.extrap_layers = (int)ceil(s.cfl_number) + 2;
 
-    dev_alloc(s.cell_start, T + 1);
-    dev_alloc(s.cell_cursor, T);
-    dev_alloc(s.scan_tmp, T / 2048 + 2);
-    dev_alloc(s.phi_liq, T);
-    dev_alloc(s.phi_sol, T);
-    dev_alloc(s.sol_center, T);
-    dev_alloc(s.vel, 3 * T);
-    dev_alloc(s.saved, 3 * T);
-    dev_alloc(s.weight, 3 * T);
-    dev_alloc(s.valid, 3 * T);
-    dev_alloc(s.layer, 3 * T);
-    dev_alloc(s.fstate, 3 * T);
-    dev_alloc(s.viscosity, T);
-    dev_alloc(s.pressure, T);
-    dev_alloc(s.maxvel_dev, 1);
-    dev_alloc(s.pcoef, T);
-    dev_alloc(s.cg_x, 3 * T);
-    dev_alloc(s.cg_r, 3 * T);
-    dev_alloc(s.cg_s, 3 * T);
-    dev_alloc(s.cg_q, 3 * T);
-    dev_alloc(s.cg_z, 3 * T);
-    dev_alloc(s.cg_w, 3 * T);
-    dev_alloc(s.vvol, 7 * T);
-    dev_alloc(s.vnode, 7 * T);
-    dev_alloc(s.vvalid, T);
-    dev_alloc(s.vcoef, 4 * T);
-    dev_alloc(s.vdiag, 3 * T);
-    dev_alloc(s.ext_flag, (size_t)g.nblocks); dev_alloc(s.ext_flag2, (size_t)g.nblocks);
-    dev_alloc(s.ext_list, (size_t)g.nblocks); dev_alloc(s.ext_count, 1);
-    dev_alloc(s.blk_flag, (size_t)g.nblocks);
-    dev_alloc(s.blk_list, (size_t)g.nblocks);
-    dev_alloc(s.blk_count, 1);
-    dev_alloc(s.unk_count, 1);
-    dev_alloc(s.cell_list, T);
-    dev_alloc(s.cell_count, 1);
-    dev_alloc(s.part, 6 * (size_t)FLIP_CG_MAXGRID);
-    dev_alloc(s.cgst, 2);
+    dev_alloc(s, s.cell_start, T + 1);
+    dev_alloc(s, s.cell_cursor, T);
+    dev_alloc(s, s.scan_tmp, T / 2048 + 2);
+    dev_alloc(s, s.phi_liq, T);
+    dev_alloc(s, s.phi_sol, T);
+    dev_alloc(s, s.sol_center, T);
+    dev_alloc(s, s.vel, 3 * T);
+    dev_alloc(s, s.saved, 3 * T);
+    dev_alloc(s, s.weight, 3 * T);
+    dev_alloc(s, s.valid, 3 * T);
+    dev_alloc(s, s.layer, 3 * T);
+    dev_alloc(s, s.fstate, 3 * T);
+    dev_alloc(s, s.viscosity, T);
+    dev_alloc(s, s.pressure, T);
+    dev_alloc(s, s.maxvel_dev, 1);
+    dev_alloc(s, s.pcoef, T);
+    dev_alloc(s, s.cg_x, 3 * T);
+    dev_alloc(s, s.cg_r, 3 * T);
+    dev_alloc(s, s.cg_s, 3 * T);
+    dev_alloc(s, s.cg_q, 3 * T);
+    dev_alloc(s, s.cg_z, 3 * T);
+    dev_alloc(s, s.cg_w, 3 * T);
+    dev_alloc(s, s.vvol, 7 * T);
+    dev_alloc(s, s.vnode, 7 * T);
+    dev_alloc(s, s.vvalid, T);
+    dev_alloc(s, s.vcoef, 4 * T);
+    dev_alloc(s, s.vdiag, 3 * T);
+    dev_alloc(s, s.ext_flag, (size_t)g.nblocks); dev_alloc(s, s.ext_flag2, (size_t)g.nblocks);
+    dev_alloc(s, s.ext_list, (size_t)g.nblocks); dev_alloc(s, s.ext_count, 1);
+    dev_alloc(s, s.blk_flag, (size_t)g.nblocks);
+    dev_alloc(s, s.blk_list, (size_t)g.nblocks);
+    dev_alloc(s, s.blk_count, 1);
+    dev_alloc(s, s.unk_count, 1);
+    dev_alloc(s, s.cell_list, T);
+    dev_alloc(s, s.cell_count, 1);
+    dev_alloc(s, s.part, 6 * (size_t)FLIP_MAX_RANKS * FLIP_CG_MAXGRID);
+    dev_alloc(s, s.part_peers, FLIP_MAX_RANKS);
+    dev_alloc(s, s.link, 1);
+    dev_alloc(s, s.link_peers, FLIP_MAX_RANKS);
+    dev_alloc(s, s.cuts, 1);
+    dev_alloc(s, s.plane_count, (size_t)nk + 2);
+    dev_alloc(s, s.cgst, 2);
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
     CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
     *s.count_host = 0;
     *s.maxvel_host = 0;
-    dist_setup_slab(s);
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
     // initial solid: none (phi = +large everywhere) until flip_set_solid_sdf; viscosity 1.0
     // like the reference's initialize (src/fluidsimulation.cpp:39)
 }
 
 static void free_particles(Sim &s) {
     for (int b = 0; b < 2; b++) {
-        for (int f = 0; f < 6; f++) { if (s.p[b][f]) cudaFree(s.p[b][f]); s.p[b][f] = 0; }
-        if (s.pid[b]) cudaFree(s.pid[b]);
-        s.pid[b] = 0;
+        for (int f = 0; f < 6; f++) heap_free(s, s.p[b][f]);
+        heap_free(s, s.pid[b]);
     }
-    if (s.cell_of) cudaFree(s.cell_of);
-    s.cell_of = 0;
+    heap_free(s, s.cell_of);
     s.cap = 0;
 }
 
@@ -98,10 +103,10 @@ void sim_reserve_particles(Sim &s, long long n) {
     free_particles(s);
     long long cap = n + n / 8 + 1024;
     for (int b = 0; b < 2; b++) {
-        for (int f = 0; f < 6; f++) dev_alloc(s.p[b][f], (size_t)cap);
-        dev_alloc(s.pid[b], (size_t)cap);
+        for (int f = 0; f < 6; f++) dev_alloc(s, s.p[b][f], (size_t)cap);
+        dev_alloc(s, s.pid[b], (size_t)cap);
     }
-    dev_alloc(s.cell_of, 2 * (size_t)cap);
+    dev_alloc(s, s.cell_of, 2 * (size_t)cap);
     s.cap = cap;
 }
 
@@ -114,13 +119,7 @@ void sim_free(Sim &s) {
     for (int q = 0; q < 4; q++) if (s.user_ev[q]) { cudaEventDestroy((cudaEvent_t)s.user_ev[q]); s.user_ev[q] = 0; }
     try { dist_shutdown(s); } catch (...) {}
     viscosity_free(s);
-    free_particles(s);
-    void *ptrs[] = {s.cell_start, s.cell_cursor, s.scan_tmp, s.phi_liq, s.phi_sol, s.sol_center, s.vel, s.saved,
-                    s.weight, s.valid, s.layer, s.fstate, s.viscosity, s.pressure, s.maxvel_dev, s.pcoef, s.cg_x,
-                    s.cg_r, s.cg_s, s.cg_q, s.cg_z, s.cg_w, s.vvol, s.vnode, s.vvalid, s.vcoef, s.vdiag, s.blk_flag, s.blk_list,
-                    s.blk_count, s.unk_count, s.cell_list, s.cell_count, s.part, s.cgst, s.ext_flag, s.ext_flag2, s.ext_list,
-                    s.ext_count};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    s.heap.destroy();   // every device buffer of the handle
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
     if (s.count_host) cudaFreeHost(s.count_host);
     if (s.maxvel_host) cudaFreeHost(s.maxvel_host);
@@ -536,10 +535,10 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "maxit_scale") { s.pressure_maxit_scale = (int)value; s.visc_maxit_scale = (int)value; }
     else if (n == "cg_chunk") s.cg_chunk = (int)value;
     else if (n == "use_graphs") s.use_graphs = (int)value;
-    else if (n == "cg_variant") { s.cg_variant_pressure = s.cg_variant_viscosity = (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
-    else if (n == "cg_variant_pressure") { s.cg_variant_pressure = (int)value; s.cg_graph_chunk[0] = -1; }
-    else if (n == "cg_variant_viscosity") { s.cg_variant_viscosity = (int)value; s.cg_graph_chunk[1] = -1; }
-    else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; for (int q = 0; q < 2; q++) s.cg_graph_chunk[q] = -1; }
+    else if (n == "cg_variant") { s.cg_variant_pressure = s.cg_variant_viscosity = (int)value; }
+    else if (n == "cg_variant_pressure") { s.cg_variant_pressure = (int)value; }
+    else if (n == "cg_variant_viscosity") { s.cg_variant_viscosity = (int)value; }
+    else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; s.xch_epoch++; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
     else if (n == "viscosity_warm_start") s.visc_warm_start = (int)value;
     else if (n == "mg_sweeps") s.mg_sweeps = (int)value;
@@ -551,8 +550,8 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_levels") s.mg_levels = (int)value;
     else if (n == "mg_flexible") s.mg_flexible = (int)value;
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
-    else if (n == "dist_min_unknowns") s.dist_min_unknowns = (long long)value;
-    else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // back to NCCL for the per-iteration exchanges
+    else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // unmap the peers: plain replicas again
+    else if (n == "xch_timeout_s") s.xch_timeout_s = value;                    // takes effect at the next flip_dist_p2p_import
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;

@@ -15,6 +15,7 @@
 // launch writes, and nothing goes back to the host except a poll every `cg_chunk` iterations.
 #pragma once
 #include "sim.h"
+#include "xch.h"
 
 #define CG_THREADS 512  // one thread per cell of an 8x8x8 block
 
@@ -54,6 +55,18 @@ FLIP_D double reduce_partials(const double *__restrict__ part, int n, double *sm
     return cta_reduce<MAX>(v, sm);
 }
 
+// Partials of reduction `kind` live at part[kind * nranks * G ...): G slots per rank, rank-major.  The producing CTA
+// stores its value into EVERY rank's array (one 8-byte NVLink store per peer), consumers re-reduce all nranks * G values
+// in that fixed order: bit-identical scalars on every rank, no all-reduce kernel.
+#define PART_STORE(P, kind, value)                                                                         \
+    do {                                                                                                   \
+        const size_t _o = ((size_t)(kind) * (P).X.nranks + (P).X.rank) * gridDim.x + blockIdx.x;           \
+        if ((P).X.nranks == 1) (P).part[_o] = (value);                                                     \
+        else for (int _p = 0; _p < (P).X.nranks; _p++) ((volatile double *)(P).part_peers[_p])[_o] = (value); \
+    } while (0)
+#define PART_PTR(P, kind) ((P).part + (size_t)(kind) * (P).X.nranks * gridDim.x)
+#define PART_N(P) ((P).X.nranks * (int)gridDim.x)
+
 struct CGParams {
     Grid g;
     const int *blk_list;
@@ -62,7 +75,9 @@ struct CGParams {
     const int *cell_count;
     double *x, *r, *s, *q;     // [NC*total]
     double *z;                 // preconditioned residual (multigrid mode), or null for the diagonal
-    double *part;              // [3*gridDim]: s.q | r.z | max|r|
+    double *part;              // reduction partials, kind-major: part[kind * nranks * G + rank * G + cta]
+    double *const *part_peers; // device table [nranks]: `part` of every rank (sharded solves push their partials to all)
+    Xch X;                     // exchange context (nranks == 1: single GPU)
     CGState *st;               // [2]
     int strict;                // 1: converged when max|r| < tol (pressure), 0: <= tol (viscosity)
     int flexible;              // multigrid mode: Polak-Ribiere beta = -(q.z)/(s.q), robust to an inexact V-cycle
@@ -82,6 +97,7 @@ struct DiagViscosity {
 template <int NC, class Diag, bool KEEPX>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag, double *__restrict__ bmax_part) {
     __shared__ double sm[CG_THREADS / 32];
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
     double rz = 0.0, bm = 0.0;
@@ -102,17 +118,19 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag, d
     rz = cta_reduce<false>(rz, sm);
     bm = cta_reduce<true>(bm, sm);
     if (threadIdx.x == 0) {
-        P.part[gridDim.x + blockIdx.x] = rz;
+        PART_STORE(P, 1, rz);
         // with a warm start max|b| (the tolerance reference) was measured before r became b - A x0
-        if (!KEEPX) P.part[2 * gridDim.x + blockIdx.x] = bm;
-        else P.part[3 * gridDim.x + blockIdx.x] = bm;   // max|r0|, informational
+        if (!KEEPX) PART_STORE(P, 2, bm);
+        else PART_STORE(P, 3, bm);   // max|r0|, informational
     }
+    xch_leave(P.X, true);
 }
 
 // max|b| partials only (warm start: the relative tolerance refers to b, not to r0)
 template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
     double bm = 0.0;
@@ -122,7 +140,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
             if (diag(m, id) != 0.0f) bm = fmax(bm, fabs(P.r[(size_t)m * g.total + id]));
     }
     bm = cta_reduce<true>(bm, sm);
-    if (threadIdx.x == 0) P.part[2 * gridDim.x + blockIdx.x] = bm;
+    if (threadIdx.x == 0) PART_STORE(P, 2, bm);
+    xch_leave(P.X, true);
 }
 
 // Warm start (x0 != 0): k_cg_guess puts the guess into s (so the phase-A kernel computes q = A x0),
@@ -158,9 +177,11 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_guess_residual(CGParams P, Di
 static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int nparts, double tol_abs, double tol_rel, int maxit,
                                                                  int warm) {
     __shared__ double sm[CG_THREADS / 32];
-    double rho = reduce_partials<false>(P.part + nparts, nparts, sm);
-    double bmax = reduce_partials<true>(P.part + 2 * nparts, nparts, sm);
-    double r0max = warm ? reduce_partials<true>(P.part + 3 * nparts, nparts, sm) : bmax;
+    if (!xch_enter(P.X)) return;
+    const int NP = P.X.nranks * nparts;   // launched with one CTA: the producers' grid size is passed in
+    double rho = reduce_partials<false>(P.part + (size_t)NP, NP, sm);
+    double bmax = reduce_partials<true>(P.part + 2 * (size_t)NP, NP, sm);
+    double r0max = warm ? reduce_partials<true>(P.part + 3 * (size_t)NP, NP, sm) : bmax;
     if (threadIdx.x == 0) {
         CGState st;
         st.rho = rho; st.resid = r0max; st.bmax = bmax;
@@ -180,6 +201,7 @@ static __global__ void __launch_bounds__(CG_THREADS) k_cg_begin(CGParams P, int 
         P.st[0] = st;
         P.st[1] = st;
     }
+    xch_leave(P.X, false);
 }
 
 // phase B: alpha = rho / s.q;  x += alpha s;  r -= alpha q;  partials of r.(M^-1 r) and max|r|
@@ -188,8 +210,9 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag,
     __shared__ double sm[CG_THREADS / 32];
     const CGState st = P.st[parity];
     if (st.done) return;
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
-    double sq = reduce_partials<false>(P.part, gridDim.x, sm);
+    double sq = reduce_partials<false>(PART_PTR(P, 0), PART_N(P), sm);
     double alpha = st.rho / sq;
     int nc = *P.cell_count;
     double rz = 0.0, rm = 0.0;
@@ -219,9 +242,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag,
     rz = cta_reduce<false>(rz, sm);
     rm = cta_reduce<true>(rm, sm);
     if (threadIdx.x == 0) {
-        if (!MG) P.part[gridDim.x + blockIdx.x] = rz;
-        P.part[2 * gridDim.x + blockIdx.x] = rm;
+        if (!MG) PART_STORE(P, 1, rz);
+        PART_STORE(P, 2, rm);
     }
+    xch_leave(P.X, true);
 }
 
 // multigrid mode: partials of r.z after the V-cycle
@@ -229,6 +253,7 @@ template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     if (parity >= 0 && P.st[parity].done) return;
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
     // at start-up (parity < 0) there is no q yet, and the fourth partial array still holds max|r0| of a warm start
@@ -247,9 +272,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
     rz = cta_reduce<false>(rz, sm);
     if (flex) qz = cta_reduce<false>(qz, sm);
     if (threadIdx.x == 0) {
-        P.part[gridDim.x + blockIdx.x] = rz;
-        if (flex) P.part[3 * gridDim.x + blockIdx.x] = qz;
+        PART_STORE(P, 1, rz);
+        if (flex) PART_STORE(P, 3, qz);
     }
+    xch_leave(P.X, true);
 }
 
 // multigrid mode, start-up: x = 0, r = masked b, partial max|b|   (then V-cycle, k_cg_dot, k_cg_start)
@@ -258,6 +284,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
 template <int NC, class Diag, bool KEEPX = false>
 __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
     double bm = 0.0;
@@ -272,7 +299,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag
         }
     }
     bm = cta_reduce<true>(bm, sm);
-    if (threadIdx.x == 0) P.part[(KEEPX ? 3 : 2) * gridDim.x + blockIdx.x] = bm;
+    if (threadIdx.x == 0) PART_STORE(P, (KEEPX ? 3 : 2), bm);
+    xch_leave(P.X, true);
 }
 
 template <int NC>
@@ -297,9 +325,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
         if (blockIdx.x == 0 && threadIdx.x == 0) P.st[parity ^ 1] = st;
         return;
     }
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
-    double rho_new = reduce_partials<false>(P.part + gridDim.x, gridDim.x, sm);
-    double rmax = reduce_partials<true>(P.part + 2 * gridDim.x, gridDim.x, sm);
+    double rho_new = reduce_partials<false>(PART_PTR(P, 1), PART_N(P), sm);
+    double rmax = reduce_partials<true>(PART_PTR(P, 2), PART_N(P), sm);
     bool conv = P.strict ? (rmax < st.tol) : (rmax <= st.tol);
     bool bad = !(rmax == rmax) || !(rho_new == rho_new);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -312,12 +341,12 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
         if (bad) nx.fail = 1;
         P.st[parity ^ 1] = nx;
     }
-    if (conv || bad) return;
+    if (conv || bad) { xch_leave(P.X, false); return; }
     double beta = rho_new / st.rho;
     if (MG && P.flexible) {
         // beta = z_new.(r_new - r_old) / rho_old with r_new - r_old = -alpha q and alpha = rho_old / s.q
-        double sq = reduce_partials<false>(P.part, gridDim.x, sm);
-        double qz = reduce_partials<false>(P.part + 3 * gridDim.x, gridDim.x, sm);
+        double sq = reduce_partials<false>(PART_PTR(P, 0), PART_N(P), sm);
+        double qz = reduce_partials<false>(PART_PTR(P, 3), PART_N(P), sm);
         beta = -qz / sq;
     }
     int nc = *P.cell_count;
@@ -340,6 +369,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_direction(CGParams P, Diag di
             P.s[o] = (MG ? zv[m] : zv[m] / (double)d) + beta * sv[m];
         }
     }
+    xch_leave(P.X, false);
 }
 
 // zero a [NC*total] double field on the cells of the listed blocks
@@ -357,27 +387,33 @@ __global__ void __launch_bounds__(CG_THREADS) k_clear_blocks(Grid g, const int *
 
 // ---- active block list -------------------------------------------------------------------
 // flag[b] = 1 if any of the NC diagonal fields is non-zero inside block b
+// unknowns (optional): total number of non-zero diagonals of the whole system (integer atomics: exact)
 template <int NC, class Diag>
-__global__ void __launch_bounds__(CG_THREADS) k_flag_blocks(Grid g, Diag diag, int *__restrict__ flag) {
+__global__ void __launch_bounds__(CG_THREADS) k_flag_blocks(Grid g, Diag diag, int *__restrict__ flag, int *__restrict__ unknowns) {
     __shared__ int any;
     if (threadIdx.x == 0) any = 0;
     __syncthreads();
     BlockCell c = block_cell(g, blockIdx.x, threadIdx.x);
-    bool nz = false;
+    int mine = 0;
     if (c.inside) {
         int id = gidx(g, c.i, c.j, c.k);
-        for (int m = 0; m < NC; m++) nz = nz || diag(m, id) != 0.0f;
+        for (int m = 0; m < NC; m++) mine += diag(m, id) != 0.0f ? 1 : 0;
     }
-    if (nz) any = 1;  // benign same-value race
+    if (mine) any = 1;  // benign same-value race
     __syncthreads();
     if (threadIdx.x == 0) flag[blockIdx.x] = any;
+    if (unknowns && any) {   // uniform across the CTA
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(unknowns, mine);
+    }
 }
 
 // single CTA, ordered compaction (ascending block id => deterministic CTA/block assignment)
 static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__restrict__ flag, int n, int *__restrict__ list,
-                                                         int *__restrict__ count, int lo, int hi) {
+                                                         int *__restrict__ count) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
+    const int lo = 0, hi = n;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -409,22 +445,6 @@ static __global__ void __launch_bounds__(1024) k_compact_blocks(const int *__res
     if (threadIdx.x == 0) *count = carry_s;
 }
 
-// number of unknowns = non-zero diagonals on the active blocks (integer atomics: exact)
-template <int NC, class Diag>
-__global__ void __launch_bounds__(CG_THREADS) k_count_unknowns(Grid g, const int *__restrict__ list,
-                                                                const int *__restrict__ count, Diag diag, int *__restrict__ out) {
-    int nb = *count;
-    int mine = 0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, list[b], threadIdx.x);
-        if (!c.inside) continue;
-        int id = gidx(g, c.i, c.j, c.k);
-        for (int m = 0; m < NC; m++) mine += diag(m, id) != 0.0f ? 1 : 0;
-    }
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
-}
-
 // ---- compact cell list -------------------------------------------------------------------
 // On the bench scene only ~23 % of the cells of an active block hold an unknown (ncu: warps half
 // empty, kernels latency bound).  The CG kernels therefore iterate over a compact, block-ordered
@@ -432,13 +452,14 @@ __global__ void __launch_bounds__(CG_THREADS) k_count_unknowns(Grid g, const int
 // because the order is (block, then cell inside the block).
 template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cell_counts(Grid g, const int *__restrict__ list, const int *__restrict__ count,
-                                                             Diag diag, int *__restrict__ per_block) {
+                                                             Diag diag, int *__restrict__ per_block, const Cuts *__restrict__ cuts, int rank) {
     __shared__ int wsum[CG_THREADS / 32];
     int nb = *count;
+    const int k0 = cuts ? cuts->c[0][rank] : 0, k1 = cuts ? cuts->c[0][rank + 1] : g.nk + 1;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         BlockCell c = block_cell(g, list[b], threadIdx.x);
         bool has = false;
-        if (c.inside) {
+        if (c.inside && c.k >= k0 && c.k < k1) {
             int id = gidx(g, c.i, c.j, c.k);
             for (int m = 0; m < NC; m++) has = has || diag(m, id) != 0.0f;
         }
@@ -492,15 +513,17 @@ static __global__ void __launch_bounds__(1024) k_scan_small(int *__restrict__ v,
 
 template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cell_fill(Grid g, const int *__restrict__ list, const int *__restrict__ count,
-                                                           Diag diag, const int *__restrict__ offset, int *__restrict__ cells) {
+                                                           Diag diag, const int *__restrict__ offset, int *__restrict__ cells,
+                                                           const Cuts *__restrict__ cuts, int rank) {
     __shared__ int wsum[CG_THREADS / 32];
     int nb = *count;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k0 = cuts ? cuts->c[0][rank] : 0, k1 = cuts ? cuts->c[0][rank + 1] : g.nk + 1;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         BlockCell c = block_cell(g, list[b], threadIdx.x);
         bool has = false;
         int id = 0;
-        if (c.inside) {
+        if (c.inside && c.k >= k0 && c.k < k1) {
             id = gidx(g, c.i, c.j, c.k);
             for (int m = 0; m < NC; m++) has = has || diag(m, id) != 0.0f;
         }
@@ -520,42 +543,56 @@ static inline int cg_grid(const Sim &s) {
     return gsz > FLIP_CG_MAXGRID ? FLIP_CG_MAXGRID : gsz;
 }
 
+// block list of a whole (replicated) level: every rank builds the same list
 template <int NC, class Diag>
 static void build_block_list_on(Sim &s, const Grid &g, Diag diag, int *flag, int *list, int *count) {
     auto kflag = &k_flag_blocks<NC, Diag>;
-    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, flag);
-    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)flag, g.nblocks, list, count, 0, g.nblocks);
+    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, flag, (int *)nullptr);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)flag, g.nblocks, list, count);
     s.kernel_launches += 2;
     KERNEL_CHECK();
 }
 
+// Work lists of a solve: the active 8x8x8 blocks of the WHOLE system (every rank builds the same list) and the compact,
+// block-ordered list of the cells that hold at least one unknown inside this rank's slab of k-planes (all of them on one
+// GPU).  s.unk_count = unknowns of the whole system.
 template <int NC, class Diag>
 static void build_block_list(Sim &s, Diag diag) {
     const Grid &g = s.g;
+    const Cuts *cuts = xch_cuts(s);          // null on one GPU
+    const int rank = xch_rank(s);
     auto kflag = &k_flag_blocks<NC, Diag>;
-    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag);
-    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count,
-                     s.bz0 * g.nbx * g.nby, s.bz1 * g.nbx * g.nby);
-    // compact cell list of this solve
+    CUDA_CHECK(cudaMemsetAsync(s.unk_count, 0, sizeof(int), s.stream));
+    FLIP_LAUNCH_SYNC(kflag, g.nblocks, CG_THREADS, s.stream, g, diag, s.blk_flag, s.unk_count);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.blk_flag, g.nblocks, s.blk_list, s.blk_count);
     auto kcc = &k_cell_counts<NC, Diag>;
     auto kcf = &k_cell_fill<NC, Diag>;
-    FLIP_LAUNCH_SYNC(kcc, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.blk_flag);
+    FLIP_LAUNCH_SYNC(kcc, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.blk_flag, cuts, rank);
     FLIP_LAUNCH_SYNC(k_scan_small, 1, 1024, s.stream, s.blk_flag, (const int *)s.blk_count, s.cell_count);
     FLIP_LAUNCH_SYNC(kcf, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag,
-                     (const int *)s.blk_flag, s.cell_list);
-    s.kernel_launches += 3;
-    auto kcount = &k_count_unknowns<NC, Diag>;
-    CUDA_CHECK(cudaMemsetAsync(s.unk_count, 0, sizeof(int), s.stream));
-    FLIP_LAUNCH_SYNC(kcount, cg_grid(s), CG_THREADS, s.stream, g, (const int *)s.blk_list, (const int *)s.blk_count, diag, s.unk_count);
-    dist_allreduce_int(s, s.unk_count);
-    s.kernel_launches += 3;
+                     (const int *)s.blk_flag, s.cell_list, cuts, rank);
+    s.kernel_launches += 5;
     KERNEL_CHECK();
 }
 
-// Generic driver.  `apply(parity)` launches the phase-A kernel (q = A s and the s.q partials).
-// On one GPU a chunk of `cg_chunk` iterations (3 kernels each) is captured ONCE into a CUDA graph
-// per solver (all kernel arguments are pointers into the handle's own buffers and never change) and
-// replayed; convergence is decided on the device, the host only polls the 64-byte state per chunk.
+// CGParams of a solve on the handle's own buffers
+static CGParams cg_params(Sim &s, int strict) {
+    CGParams P;
+    P.g = s.g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
+    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
+    P.part = s.part; P.part_peers = s.part_peers; P.X = xch_of(s); P.st = s.cgst; P.strict = strict; P.flexible = 0;
+    return P;
+}
+
+// A CUDA graph of an iteration chunk is only valid for the exchange set-up it was captured under
+static inline unsigned long long cg_graph_tag(Sim &s, int chunk, int variant) {
+    return (unsigned long long)chunk * 4 + variant + ((unsigned long long)s.xch_epoch << 20);
+}
+
+// Generic driver.  `apply(parity)` launches the phase-A kernel (q = A s and the s.q partials); on several ranks it also
+// pushes the ghost planes of s first (the closure decides).  A chunk of `cg_chunk` iterations (3 kernels each) is
+// captured ONCE into a CUDA graph per solver (all kernel arguments are pointers into the handle's own buffers and never
+// change) and replayed; convergence is decided on the device, the host only polls the 64-byte state per chunk.
 template <int NC, class Diag, class ApplyFn>
 static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply,
                       int graph_slot = -1, const float *guess = nullptr) {
@@ -581,9 +618,6 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
         FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag, (double *)nullptr);
         s.kernel_launches += 1;
     }
-    dist_reduce_partials(s, P.part + G, G, false);
-    dist_reduce_partials(s, P.part + 2 * G, G, true);
-    dist_reduce_partials(s, P.part + 3 * G, G, true);
     FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, guess ? 1 : 0);
     s.kernel_launches += 1;
     KERNEL_CHECK();
@@ -592,26 +626,27 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;
             apply(parity);
-            dist_reduce_partials(s, P.part, G, false);
             FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
-            dist_reduce_pair(s, P.part + G, P.part + 2 * G, G, nullptr, 0);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
         }
     };
 #ifndef FLIP_CPU_EMU
-    // NCCL calls are stream-captured with the kernels (multi-GPU: use_graphs >= 2 opts in)
-    bool use_graph = s.use_graphs && (s.nranks == 1 || dist_p2p_active(s) || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
-    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk)) {
+    bool use_graph = s.use_graphs && graph_slot >= 0 && graph_slot < 2;
+    const unsigned long long tag = cg_graph_tag(s, chunk, 0);
+    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_tag[graph_slot] != tag)) {
         if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
         cudaGraph_t graph = nullptr;
+        long long keep = s.kernel_launches;
         CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         launch_chunk();
         CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        s.cg_graph_launches[graph_slot] = s.kernel_launches - keep + 2 * chunk;
+        s.kernel_launches = keep;
         cudaGraphExec_t exec = nullptr;
         CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
         CUDA_CHECK(cudaGraphDestroy(graph));
         s.cg_graph[graph_slot] = (void *)exec;
-        s.cg_graph_chunk[graph_slot] = chunk;
+        s.cg_graph_tag[graph_slot] = tag;
     }
 #else
     bool use_graph = false;
@@ -624,53 +659,10 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
         h = *s.cgst_host;
         if (h.done || launched >= maxit + chunk) break;
 #ifndef FLIP_CPU_EMU
-        if (use_graph) CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream));
+        if (use_graph) { CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream)); s.kernel_launches += s.cg_graph_launches[graph_slot]; }
         else
 #endif
-            launch_chunk();
-        s.kernel_launches += 3 * chunk;
-        KERNEL_CHECK();
-        launched += chunk;
-    }
-    return h;
-}
-
-// Same driver with a general preconditioner: `precond(st)` launches kernels that compute
-// P.z = M^-1 P.r on the active blocks (st = CGState slot to test for `done`, or null at start-up).
-template <int NC, class Diag, class ApplyFn, class PrecondFn>
-static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply,
-                         PrecondFn precond) {
-    int G = cg_grid(s);
-    auto kinit = &k_cg_init_mg<NC, Diag>;
-    auto kstart = &k_cg_start_mg<NC>;
-    auto kdot = &k_cg_dot<NC, Diag>;
-    auto kupdate = &k_cg_update<NC, Diag, true>;
-    auto kdir = &k_cg_direction<NC, Diag, true>;
-    FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, P, diag);
-    precond((const CGState *)nullptr);
-    FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, -1);
-    FLIP_LAUNCH(kstart, G, CG_THREADS, s.stream, P);
-    FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, 0);
-    s.kernel_launches += 4;
-    KERNEL_CHECK();
-    int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
-    CGState h;
-    int launched = 0;
-    while (true) {
-        CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
-        CUDA_CHECK(cudaStreamSynchronize(s.stream));
-        h = *s.cgst_host;
-        if (s.verbose > 1) printf("\t\tmg-pcg iteration %d max|r| %.3e (tol %.3e)\n", h.iter, h.resid, h.tol), fflush(stdout);
-        if (h.done || launched >= maxit + chunk) break;
-        for (int it = 0; it < chunk; it++) {
-            int parity = it & 1;
-            apply(parity);
-            FLIP_LAUNCH_SYNC(kupdate, G, CG_THREADS, s.stream, P, diag, parity);
-            precond((const CGState *)(P.st + parity));
-            FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, parity);
-            FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
-            s.kernel_launches += 4;
-        }
+        { launch_chunk(); s.kernel_launches += 2 * chunk; }
         KERNEL_CHECK();
         launched += chunk;
     }
@@ -687,13 +679,12 @@ static CGState run_cg_mg(Sim &s, CGParams P, Diag diag, double tol_abs, double t
 // Two kernels per iteration instead of three and ONE point where scalars are needed:
 //   K1 (k_cg2_step)  reduces the partials of gamma, delta and max|r| left by the previous iteration,
 //                    decides convergence, updates p, s, x, r, u in one pass and leaves the partials
-//                    of the new gamma and max|r| (ping-pong buffers: other CTAs still read the old);
+//                    of the new gamma and max|r| (ping-pong kinds: other CTAs still read the old);
 //   K2 (phase-A stencil kernel, unchanged, with s:=u and q:=w) computes w = A u and the partials of
 //                    delta.
-// On several GPUs that is one 2-element sum all-reduce + one max all-reduce per iteration instead of
-// three scalar all-reduces.  Same operator, same stopping rule (max|r| against the tolerance, tested
-// on the residual BEFORE each update), same converged solution as run_cg.
-// Partials: [0,G) delta | [G,2G) gamma(0) | [2G,3G) rmax(0) | [3G,4G) gamma(1) | [4G,5G) rmax(1)
+// Same operator, same stopping rule (max|r| against the tolerance, tested on the residual BEFORE each
+// update), same converged solution as run_cg.
+// Partial kinds: 0 delta | 1 gamma(0) | 2 rmax(0) | 3 gamma(1) | 4 rmax(1)
 // ------------------------------------------------------------------------------------------
 struct CG2Params {
     CGParams P;      // x, r, s(=p), q(=s=Ap) as in CGParams; z = u
@@ -704,6 +695,7 @@ template <int NC, class Diag>
 __global__ void __launch_bounds__(CG_THREADS) k_cg2_init(CG2Params Q, Diag diag) {
     __shared__ double sm[CG_THREADS / 32];
     const CGParams &P = Q.P;
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     int nc = *P.cell_count;
     double gam = 0.0, bm = 0.0;
@@ -725,9 +717,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_init(CG2Params Q, Diag diag)
     gam = cta_reduce<false>(gam, sm);
     bm = cta_reduce<true>(bm, sm);
     if (threadIdx.x == 0) {
-        P.part[gridDim.x + blockIdx.x] = gam;        // gamma(0)
-        P.part[2 * gridDim.x + blockIdx.x] = bm;     // rmax(0) = max|b|
+        PART_STORE(P, 1, gam);       // gamma(0)
+        PART_STORE(P, 2, bm);        // rmax(0) = max|b|
     }
+    xch_leave(P.X, true);
 }
 
 template <int NC, class Diag>
@@ -740,11 +733,10 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_step(CG2Params Q, Diag diag,
         if (blockIdx.x == 0 && threadIdx.x == 0) P.st[parity ^ 1] = st;
         return;
     }
-    const double *gpart = P.part + (parity ? 3 : 1) * G, *mpart = P.part + (parity ? 4 : 2) * G;
-    double *gnext = P.part + (parity ? 1 : 3) * G, *mnext = P.part + (parity ? 2 : 4) * G;
-    double rmax = reduce_partials<true>(mpart, G, sm);
-    double gam = reduce_partials<false>(gpart, G, sm);
-    double del = reduce_partials<false>(P.part, G, sm);
+    if (!xch_enter(P.X)) return;
+    double rmax = reduce_partials<true>(PART_PTR(P, parity ? 4 : 2), PART_N(P), sm);
+    double gam = reduce_partials<false>(PART_PTR(P, parity ? 3 : 1), PART_N(P), sm);
+    double del = reduce_partials<false>(PART_PTR(P, 0), PART_N(P), sm);
     bool conv = P.strict ? (rmax < st.tol) : (rmax <= st.tol);
     double beta = st.first ? 0.0 : gam / st.rho;
     double alpha = st.first ? gam / del : gam / (del - beta * gam / st.alpha);
@@ -759,7 +751,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_step(CG2Params Q, Diag diag,
         if (!stop) { nx.iter = st.iter + 1; nx.rho = gam; nx.alpha = alpha; nx.first = 0; }
         P.st[parity ^ 1] = nx;
     }
-    if (stop) return;
+    if (stop) { xch_leave(P.X, false); return; }
     const Grid &g = P.g;
     const bool first = st.first != 0;
     int nc = *P.cell_count;
@@ -796,11 +788,12 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_step(CG2Params Q, Diag diag,
     }
     gnew = cta_reduce<false>(gnew, sm);
     rm = cta_reduce<true>(rm, sm);
-    if (threadIdx.x == 0) { gnext[blockIdx.x] = gnew; mnext[blockIdx.x] = rm; }
+    if (threadIdx.x == 0) { PART_STORE(P, parity ? 1 : 3, gnew); PART_STORE(P, parity ? 2 : 4, rm); }
+    xch_leave(P.X, true);
 }
 
-// `apply_uw(parity)` must launch the phase-A kernel on a CGParams whose s is u (P.z) and q is w:
-// it computes w = A u and leaves the partials of u.w in part[0,G).
+// `apply_uw(parity)` must launch the phase-A kernel on a CGParams whose s is u (P.z) and q is w: it computes w = A u and
+// leaves the partials of u.w in kind 0; on several ranks it pushes the ghost planes of u first.
 template <int NC, class Diag, class ApplyFn>
 static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_rel, int maxit, ApplyFn apply_uw, int graph_slot) {
     int G = cg_grid(s);
@@ -809,39 +802,36 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
     auto kinit = &k_cg2_init<NC, Diag>;
     auto kstep = &k_cg2_step<NC, Diag>;
     FLIP_LAUNCH_SYNC(kinit, G, CG_THREADS, s.stream, Q, diag);
-    dist_reduce_partials(s, P.part + G, G, false);
-    dist_reduce_partials(s, P.part + 2 * G, G, true);
     // first CGState: reuses k_cg_begin (rho := gamma0, tolerance, trivial-rhs exits)
     FLIP_LAUNCH_SYNC(k_cg_begin, 1, CG_THREADS, s.stream, P, G, tol_abs, tol_rel, maxit, 0);
-    dist_halo_exchange(s, Q.P.z, NC);
     apply_uw(0);
-    dist_reduce_partials(s, P.part, G, false);
-    s.kernel_launches += 3;
+    s.kernel_launches += 2;
     KERNEL_CHECK();
     int chunk = s.cg_chunk < 2 ? 2 : (s.cg_chunk & ~1);
     auto launch_chunk = [&]() {
         for (int it = 0; it < chunk; it++) {
             int parity = it & 1;
             FLIP_LAUNCH_SYNC(kstep, G, CG_THREADS, s.stream, Q, diag, parity);
-            // gamma (sum), max|r| (max) and the ghost planes of u in ONE exchange
-            dist_reduce_pair(s, P.part + (parity ? 1 : 3) * G, P.part + (parity ? 2 : 4) * G, G, Q.P.z, NC);
             apply_uw(parity ^ 1);
-            dist_reduce_partials(s, P.part, G, false);
         }
     };
 #ifndef FLIP_CPU_EMU
-    bool use_graph = s.use_graphs && (s.nranks == 1 || dist_p2p_active(s) || s.use_graphs >= 2) && graph_slot >= 0 && graph_slot < 2;
-    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_chunk[graph_slot] != chunk + 1000)) {
+    bool use_graph = s.use_graphs && graph_slot >= 0 && graph_slot < 2;
+    const unsigned long long tag = cg_graph_tag(s, chunk, 1);
+    if (use_graph && (!s.cg_graph[graph_slot] || s.cg_graph_tag[graph_slot] != tag)) {
         if (s.cg_graph[graph_slot]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[graph_slot]); s.cg_graph[graph_slot] = nullptr; }
         cudaGraph_t graph = nullptr;
+        long long keep = s.kernel_launches;
         CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         launch_chunk();
         CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        s.cg_graph_launches[graph_slot] = s.kernel_launches - keep + chunk;
+        s.kernel_launches = keep;
         cudaGraphExec_t exec = nullptr;
         CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
         CUDA_CHECK(cudaGraphDestroy(graph));
         s.cg_graph[graph_slot] = (void *)exec;
-        s.cg_graph_chunk[graph_slot] = chunk + 1000;   // tag: graph of the single-reduction variant
+        s.cg_graph_tag[graph_slot] = tag;
     }
 #else
     bool use_graph = false;
@@ -854,11 +844,10 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
         h = *s.cgst_host;
         if (h.done || launched >= maxit + 2 * chunk) break;
 #ifndef FLIP_CPU_EMU
-        if (use_graph) CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream));
+        if (use_graph) { CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream)); s.kernel_launches += s.cg_graph_launches[graph_slot]; }
         else
 #endif
-            launch_chunk();
-        s.kernel_launches += 2 * chunk;
+        { launch_chunk(); s.kernel_launches += chunk; }
         KERNEL_CHECK();
         launched += chunk;
     }

@@ -1,30 +1,205 @@
-// Multi-GPU support: one process per GPU, 1-D slab decomposition along k (the slowest index, so a
-// slab and its ghost planes are contiguous in memory), NCCL over NVLink for the exchanges.
+// Multi-GPU support: one process per GPU; every rank holds the whole (bit-identical) simulation state in its own
+// 180 GB and the WORK of a substep is cut into k-slabs (k is the slowest index, so a slab and its ghost planes are
+// contiguous in memory).  Results travel by peer-memory stores over NVLink / NVSwitch straight into the other ranks'
+// copies (symmetric heap, heap.h) with per-kernel flag hand-shakes (xch.h): no NCCL call, no host round trip and no
+// packing anywhere on the substep path.  NCCL is only used here for the rendezvous (communicator creation doubles as a
+// sanity check that all ranks can talk) — torch.distributed / the host application ships the unique id and the heap
+// handles.
 //
-// What is decomposed: the two CG solves, which are > 90 % of a substep — each rank applies the
-// stencil and the vector updates on its own slab of 8x8x8 blocks, exchanges ONE ghost plane of the
-// search direction with each k-neighbour per stencil apply (three planes, U/V/W, for the viscosity
-// system) and all-reduces the CG scalars.  What is replicated: the particle and grid stages
-// (binning, SDF, P2G, extrapolation, G2P; ~2 % of a 256^3 substep) run identically on every rank —
-// they are deterministic, so the replicas stay bit-identical — and each solve ends with an
-// all-gather of the solution slabs.  SURVEY.md §8(e) describes the fully partitioned variant
-// (particle migration, halo-min/halo-add); that is the next step, see DESIGN.md.
+// What is cut into slabs (balanced by liquid cells per k-plane, re-cut every substep on the device):
+//   both CG solves (stencil applies, vector updates, dot products), multigrid levels 0 and 1 of the viscosity
+//   preconditioner (sweeps, residuals, transfers), the Galerkin products of levels 1 and 2.
+// What every rank runs in full on its own copy: multigrid levels >= 2 (small, latency bound), the grid set-up sweeps and
+// the particle stages (deterministic, so the replicas stay bit-identical).
 //
-// The reference has no multi-process path at all, so nothing here replaces
-// reference code.
+// The reference has no multi-process path at all, so nothing here replaces reference code.
 #include "sim.h"
+#include <cstring>
+
+static __global__ void k_xch_barrier(Xch X) {
+    if (!xch_enter(X)) return;
+    xch_leave(X, false);
+}
+
+struct HeapBlob {   // what one rank exports: its heap chunks
+    int rank, nchunks;
+    unsigned long long size[FLIP_HEAP_MAX_CHUNKS];
+    cudaIpcMemHandle_t handle[FLIP_HEAP_MAX_CHUNKS];
+};
+
+int dist_p2p_blob_size() { return (int)sizeof(HeapBlob); }
+
+void dist_p2p_export(Sim &s, void *out) {
+    HeapBlob b;
+    memset(&b, 0, sizeof(b));
+    b.rank = s.rank;
+    b.nchunks = (int)s.heap.chunks.size();
+    for (int c = 0; c < b.nchunks; c++) {
+        b.size[c] = s.heap.chunks[c].size;
+        CUDA_CHECK(cudaIpcGetMemHandle(&b.handle[c], s.heap.chunks[c].base));
+    }
+    memcpy(out, &b, sizeof(b));
+}
+
+static void close_peers(Sim &s) {
+    for (int r = 0; r < FLIP_MAX_RANKS; r++)
+        for (int c = 0; c < FLIP_HEAP_MAX_CHUNKS; c++) {
+            if (s.heap.peer_base[r][c] && r != s.rank) cudaIpcCloseMemHandle(s.heap.peer_base[r][c]);
+            s.heap.peer_base[r][c] = nullptr;
+        }
+}
+
+void dist_p2p_shutdown(Sim &s) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    close_peers(s);
+    s.heap.frozen = false;
+    s.sharded = false;
+    s.xch_epoch++;   // captured graphs hold the hand-shakes of the old set-up
+}
+
+void dist_p2p_import(Sim &s, const void *all_blobs) {
+    if (s.nranks < 2) return;
+    if (s.nranks > FLIP_MAX_RANKS) throw FlipError("flip_dist_p2p_import: too many ranks");
+    if (s.g.nk + 1 < 4 * s.nranks) throw FlipError("flip_dist_p2p_import: fewer than 4 k-planes per rank");
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    close_peers(s);
+    s.sharded = false;
+    const HeapBlob *blobs = (const HeapBlob *)all_blobs;
+    const int nch = (int)s.heap.chunks.size();
+    try {
+        for (int r = 0; r < s.nranks; r++) {
+            if (blobs[r].rank != r) throw FlipError("flip_dist_p2p_import: blobs are not in rank order");
+            if (blobs[r].nchunks != nch) throw FlipError("flip_dist_p2p_import: the ranks' heaps differ (same scene and calls on every rank?)");
+            for (int c = 0; c < nch; c++) {
+                if (blobs[r].size[c] != s.heap.chunks[c].size) throw FlipError("flip_dist_p2p_import: the ranks' heap chunks differ in size");
+                if (r == s.rank) { s.heap.peer_base[r][c] = s.heap.chunks[c].base; continue; }
+                void *p = nullptr;
+                CUDA_CHECK(cudaIpcOpenMemHandle(&p, blobs[r].handle[c], cudaIpcMemLazyEnablePeerAccess));
+                s.heap.peer_base[r][c] = (char *)p;
+            }
+        }
+    } catch (...) {
+        close_peers(s);   // do not leave half-opened mappings behind
+        throw;
+    }
+    s.heap.rank = s.rank; s.heap.nranks = s.nranks;
+    s.heap.frozen = true;
+    // hand-shake state: all counters equal (zero) on every rank, tables of the peers' Link / partial arrays
+    Link L;
+    memset(&L, 0, sizeof(L));
+#ifdef FLIP_CPU_EMU
+    L.timeout_cycles = (long long)(s.xch_timeout_s * 1e9);
+#else
+    int dev = 0, khz = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    L.timeout_cycles = (long long)(s.xch_timeout_s * 1e3 * (double)khz);
+#endif
+    CUDA_CHECK(cudaMemcpy(s.link, &L, sizeof(L), cudaMemcpyHostToDevice));
+    Link *lp[FLIP_MAX_RANKS];
+    double *pp[FLIP_MAX_RANKS];
+    for (int r = 0; r < FLIP_MAX_RANKS; r++) {
+        lp[r] = r < s.nranks ? s.heap.peer(r, s.link) : nullptr;
+        pp[r] = r < s.nranks ? s.heap.peer(r, s.part) : nullptr;
+    }
+    CUDA_CHECK(cudaMemcpy(s.link_peers, lp, sizeof(lp), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(s.part_peers, pp, sizeof(pp), cudaMemcpyHostToDevice));
+    s.sharded = true;
+    s.xch_epoch++;
+}
+
+Xch xch_of(Sim &s) {
+    Xch X;
+    X.local = s.link; X.peers = s.link_peers;
+    X.rank = s.sharded ? s.rank : 0;
+    X.nranks = s.sharded ? s.nranks : 1;
+    return X;
+}
+const Cuts *xch_cuts(Sim &s) { return s.sharded ? s.cuts : nullptr; }
+int xch_rank(Sim &s) { return s.sharded ? s.rank : 0; }
+
+void xch_update_cuts(Sim &s) {
+    if (!s.sharded) return;
+    FLIP_LAUNCH_SYNC(k_plane_liquid, s.g.nk, 256, s.stream, s.g, (const float *)s.phi_liq, s.plane_count);
+    FLIP_LAUNCH(k_make_cuts, 1, 32, s.stream, s.g, (const int *)s.plane_count, s.nranks, s.cuts);
+    s.kernel_launches += 2;
+    KERNEL_CHECK();
+}
+
+static PushDesc push_desc(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level, int halo) {
+    PushDesc d;
+    memset(&d, 0, sizeof(d));
+    d.src = (const char *)field;
+    for (int r = 0; r < s.nranks; r++) d.dst[r] = (char *)s.heap.peer(r, field);
+    d.plane_bytes = (size_t)g.ax * g.ay * elem;
+    d.comp_stride_bytes = (size_t)g.total * elem;
+    d.ncomp = ncomp; d.level = level; d.halo = halo; d.pz = FLIP_PZ;
+    return d;
+}
+
+static int push_grid(Sim &s, size_t bytes) {
+    long long ctas = (long long)(bytes / (256 * 16 * 2)) + 1;
+    long long cap = (long long)s.num_sms * 2;
+    return (int)(ctas < cap ? ctas : cap);
+}
+
+void xch_push_halo(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level, int halo) {
+    if (!s.sharded) return;
+    PushDesc d = push_desc(s, g, field, elem, ncomp, level, halo);
+    int G = push_grid(s, 2 * (size_t)halo * ncomp * d.plane_bytes);
+    FLIP_LAUNCH_SYNC(k_push_planes, G, 256, s.stream, xch_of(s), (const Cuts *)s.cuts, d);
+    s.kernel_launches++;
+}
+
+void xch_push_gather(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level) {
+    if (!s.sharded) return;
+    PushDesc d = push_desc(s, g, field, elem, ncomp, level, 0);
+    // a slab is at most the whole field; the usual one is 1/nranks of it
+    int G = push_grid(s, (size_t)ncomp * d.comp_stride_bytes / s.nranks * (s.nranks - 1));
+    FLIP_LAUNCH_SYNC(k_push_planes, G, 256, s.stream, xch_of(s), (const Cuts *)s.cuts, d);
+    s.kernel_launches++;
+}
+
+void xch_push_rows(Sim &s, const int *rng_dev, void *base, size_t row_bytes) {
+    if (!s.sharded) return;
+    PushDesc d;
+    memset(&d, 0, sizeof(d));
+    d.src = (const char *)base;
+    for (int r = 0; r < s.nranks; r++) d.dst[r] = (char *)s.heap.peer(r, base);
+    FLIP_LAUNCH_SYNC(k_push_rows, s.num_sms * 4, 256, s.stream, xch_of(s), rng_dev, (const char *)base, d, row_bytes);
+    s.kernel_launches++;
+}
+
+void xch_barrier(Sim &s) {
+    if (!s.sharded) return;
+    FLIP_LAUNCH_SYNC(k_xch_barrier, 1, 32, s.stream, xch_of(s));
+    s.kernel_launches++;
+}
+
+void xch_check(Sim &s) {
+    if (!s.sharded) return;
+    int status = 0;
+    CUDA_CHECK(cudaMemcpy(&status, &s.link->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status != 0)
+        throw FlipError("multi-GPU exchange timed out: a rank is missing or out of step (every rank must hold the same scene "
+                        "and make the same calls); call flip_dist_p2p_export/_import again on all ranks to re-arm");
+}
 
 #ifdef FLIP_CPU_EMU
-// the CPU emulator is single-process
-void dist_setup_slab(Sim &s) { s.bz0 = 0; s.bz1 = s.g.nbz; }
-void dist_init(Sim &, int, int nranks, const void *) { if (nranks != 1) throw FlipError("cpu-emu build is single process"); }
-void dist_shutdown(Sim &) {}
+// the CPU emulator has no NCCL: ranks are host threads of one process (tests/test_sharded_emu.py)
 void dist_get_unique_id(void *out128) { memset(out128, 0, 128); }
-void dist_reduce_partials(Sim &, double *, int, bool) {}
-void dist_halo_exchange(Sim &, double *, int) {}
-void dist_allgather_slabs(Sim &, double *, int) {}
-void dist_allreduce_int(Sim &, int *) {}
-void dist_reduce_pair(Sim &, double *, double *, int, double *, int) {}
+void dist_init(Sim &s, int rank, int nranks, const void *) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || nranks > FLIP_MAX_RANKS) throw FlipError("dist_init: bad rank / nranks");
+    dist_shutdown(s);
+    s.rank = rank; s.nranks = nranks;
+    s.heap.rank = rank; s.heap.nranks = nranks;
+    emu::force_sync() = nranks > 1;
+}
+void dist_shutdown(Sim &s) {
+    dist_p2p_shutdown(s);
+    s.rank = 0; s.nranks = 1;
+    s.heap.rank = 0; s.heap.nranks = 1;
+}
 #else
 #include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 #include <dlfcn.h>
@@ -90,12 +265,6 @@ static NcclApi &nccl_api() {
             throw FlipError(std::string(#expr) + " failed: " + ncclGetErrorString(_r));           \
     } while (0)
 
-void dist_setup_slab(Sim &s) {
-    int nbz = s.g.nbz;
-    s.bz0 = (int)((long long)nbz * s.rank / s.nranks);
-    s.bz1 = (int)((long long)nbz * (s.rank + 1) / s.nranks);
-}
-
 void dist_get_unique_id(void *out128) {
     ncclUniqueId id;
     NCCL_CHECK(ncclGetUniqueId(&id));
@@ -104,109 +273,30 @@ void dist_get_unique_id(void *out128) {
 }
 
 void dist_init(Sim &s, int rank, int nranks, const void *unique_id) {
-    if (nranks < 1 || rank < 0 || rank >= nranks) throw FlipError("dist_init: bad rank / nranks");
-    if (nranks > s.g.nbz) throw FlipError("dist_init: more ranks than 8-cell block layers along k");
+    if (nranks < 1 || rank < 0 || rank >= nranks || nranks > FLIP_MAX_RANKS) throw FlipError("dist_init: bad rank / nranks");
     dist_shutdown(s);
     s.rank = rank; s.nranks = nranks;
-    if (nranks > 1) {
+    s.heap.rank = rank; s.heap.nranks = nranks;
+    if (nranks > 1 && unique_id) {
         ncclUniqueId id;
         memcpy(&id, unique_id, 128);
         ncclComm_t comm;
         NCCL_CHECK(ncclCommInitRank(&comm, nranks, id, rank));
         s.nccl = (void *)comm;
+        // one collective on the communicator: every rank is really there before anybody maps peer memory
+        int *one = nullptr;
+        CUDA_CHECK(cudaMalloc((void **)&one, sizeof(int)));
+        CUDA_CHECK(cudaMemset(one, 0, sizeof(int)));
+        NCCL_CHECK(ncclAllReduce(one, one, 1, ncclInt, ncclSum, comm, s.stream));
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        cudaFree(one);
     }
-    dist_setup_slab(s);
 }
 
 void dist_shutdown(Sim &s) {
     dist_p2p_shutdown(s);
     if (s.nccl) { ncclCommDestroy((ncclComm_t)s.nccl); s.nccl = 0; }
     s.rank = 0; s.nranks = 1;
-    dist_setup_slab(s);
-}
-
-// part[0] = reduce(part[0..n)), part[1..n) = 0: consumers that re-reduce the n partials then see the
-// global value once the all-reduce has run on part[0]
-__global__ void __launch_bounds__(512) k_collapse_partials(double *__restrict__ part, int n, int is_max) {
-    __shared__ double sm[16];
-    double v = 0.0;
-    for (int q = threadIdx.x; q < n; q += 512) v = is_max ? fmax(v, part[q]) : v + part[q];
-    for (int o = 16; o > 0; o >>= 1) {
-        double u = __shfl_xor_sync(0xffffffffu, v, o);
-        v = is_max ? fmax(v, u) : v + u;
-    }
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = sm[0];
-    for (int w = 1; w < 16; w++) r = is_max ? fmax(r, sm[w]) : r + sm[w];
-    __syncthreads();
-    for (int q = threadIdx.x; q < n; q += 512) part[q] = (q == 0) ? r : 0.0;
-}
-
-void dist_reduce_partials(Sim &s, double *part, int n, bool is_max) {
-    if (s.nranks == 1) return;
-    if (dist_p2p_active(s)) { dist_p2p_reduce(s, part, n, is_max); return; }
-    k_collapse_partials<<<1, 512, 0, s.stream>>>(part, n, is_max ? 1 : 0);
-    s.kernel_launches++;
-    NCCL_CHECK(ncclAllReduce(part, part, 1, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)s.nccl, s.stream));
-}
-
-void dist_reduce_pair(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp) {
-    if (s.nranks == 1) return;
-    if (dist_p2p_active(s)) { dist_p2p_step(s, part_sum, part_max, n, field, ncomp); return; }
-    dist_reduce_partials(s, part_sum, n, false);
-    dist_reduce_partials(s, part_max, n, true);
-    if (field) dist_halo_exchange(s, field, ncomp);
-}
-
-void dist_allreduce_int(Sim &s, int *dev_value) {
-    if (s.nranks == 1) return;
-    NCCL_CHECK(ncclAllReduce(dev_value, dev_value, 1, ncclInt, ncclSum, (ncclComm_t)s.nccl, s.stream));
-}
-
-static inline size_t plane_elems(const Grid &g) { return (size_t)g.ax * g.ay; }
-static inline size_t plane_offset(const Grid &g, int k) { return (size_t)(k + FLIP_PZ) * plane_elems(g); }
-
-// Owned cell planes of this rank: k in [8*bz0, min(8*bz1, nk+1)).  The plane just below / above the
-// slab is the ghost layer the 7-point and the coupled-face stencils read.
-void dist_halo_exchange(Sim &s, double *field, int ncomp) {
-    if (s.nranks == 1) return;
-    if (dist_p2p_active(s)) { dist_p2p_halo(s, field, ncomp); return; }
-    const Grid &g = s.g;
-    ncclComm_t comm = (ncclComm_t)s.nccl;
-    int k0 = FLIP_B * s.bz0, k1 = FLIP_B * s.bz1;   // k1 may exceed nk+1 on the last rank (no upper neighbour then)
-    size_t pe = plane_elems(g);
-    NCCL_CHECK(ncclGroupStart());
-    for (int c = 0; c < ncomp; c++) {
-        double *f = field + (size_t)c * g.total;
-        if (s.rank > 0) {
-            NCCL_CHECK(ncclSend(f + plane_offset(g, k0), pe, ncclDouble, s.rank - 1, comm, s.stream));
-            NCCL_CHECK(ncclRecv(f + plane_offset(g, k0 - 1), pe, ncclDouble, s.rank - 1, comm, s.stream));
-        }
-        if (s.rank < s.nranks - 1) {
-            NCCL_CHECK(ncclSend(f + plane_offset(g, k1 - 1), pe, ncclDouble, s.rank + 1, comm, s.stream));
-            NCCL_CHECK(ncclRecv(f + plane_offset(g, k1), pe, ncclDouble, s.rank + 1, comm, s.stream));
-        }
-    }
-    NCCL_CHECK(ncclGroupEnd());
-}
-
-void dist_allgather_slabs(Sim &s, double *field, int ncomp) {
-    if (s.nranks == 1) return;
-    const Grid &g = s.g;
-    ncclComm_t comm = (ncclComm_t)s.nccl;
-    size_t pe = plane_elems(g);
-    NCCL_CHECK(ncclGroupStart());
-    for (int r = 0; r < s.nranks; r++) {
-        int b0 = (int)((long long)g.nbz * r / s.nranks), b1 = (int)((long long)g.nbz * (r + 1) / s.nranks);
-        int k0 = FLIP_B * b0, k1 = FLIP_B * b1;
-        if (k1 > g.nk + 1) k1 = g.nk + 1;
-        if (k1 <= k0) continue;
-        for (int c = 0; c < ncomp; c++) {
-            double *f = field + (size_t)c * g.total + plane_offset(g, k0);
-            NCCL_CHECK(ncclBroadcast(f, f, (size_t)(k1 - k0) * pe, ncclDouble, r, comm, s.stream));
-        }
-    }
-    NCCL_CHECK(ncclGroupEnd());
+    s.heap.rank = 0; s.heap.nranks = 1;
 }
 #endif

@@ -191,7 +191,7 @@ void extrapolate_velocity(Sim &s) {
     const Grid &g = s.g;
     FLIP_LAUNCH_SYNC(k_extrap_init, g.nblocks, CG_THREADS, s.stream, g, (const unsigned char *)s.valid, s.layer, s.ext_flag);
     FLIP_LAUNCH(k_extrap_dilate, cdiv(g.nblocks, 256), 256, s.stream, g, (const int *)s.ext_flag, s.ext_flag2);
-    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.ext_flag2, g.nblocks, s.ext_list, s.ext_count, 0, g.nblocks);
+    FLIP_LAUNCH_SYNC(k_compact_blocks, 1, 1024, s.stream, (const int *)s.ext_flag2, g.nblocks, s.ext_list, s.ext_count);
     int G = s.num_sms * 4 < g.nblocks ? s.num_sms * 4 : g.nblocks;
     for (int L = 1; L <= s.extrap_layers; L++) {
         FLIP_LAUNCH(k_extrap_layer, G, CG_THREADS, s.stream, g, (const int *)s.ext_list, (const int *)s.ext_count, s.vel, s.layer, L);

@@ -24,6 +24,7 @@
 //                 CG stays fp64), symmetric, so plain CG remains valid.
 #pragma once
 #include "cg.h"
+#include "scan.h"
 
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
@@ -88,8 +89,13 @@ struct GLevel {
     float *pn = 0;        // [3T] sum of the prolongation weights of a face's coarse parents that exist
     float *x[2] = {0, 0}, *b = 0, *r = 0;   // [3T]
     int *blk_flag = 0, *blk_list = 0, *blk_count = 0;
-    int *rows = 0;        // [nrows] m*T + id, grouped by block, component-major inside a block
+    int *rows = 0;        // [nrows] m*T + id, k-PLANE major (a rank's slab of planes is one contiguous row range), then
+                          //         8x8 tile of the plane, component, cell of the tile
     int *rowmap = 0;      // [3T] inverse of rows (-1 = not an unknown)
+    int *tile_off = 0;    // [ntiles + 1] first row of every (plane, tile); ntiles = 8 nbz * nby * nbx
+    int *scan_tmp = 0;
+    int ntiles = 0;
+    int *rng = 0;         // device [4]: {first, end} row of this rank's slab, then {0, nrows}
     int *nrows_dev = 0;
     int nrows = 0;
     size_t cap = 0;       // rows S is allocated for
@@ -119,6 +125,8 @@ struct GLevelDev {
     const float *diag;
     const int *rows;
     const int *nrows;
+    const int *rng;      // {first, end} row this launch works on (the rank's slab on a sharded level, else all rows)
+    Xch X;               // exchange context; nranks == 1 on replicated levels and on one GPU
     const float *S;
     const float *wj;     // [nrows] smoothing weights
     const int *offs;     // [3 * GMG_STRIDE] element offset of every slot, per row component (0 for padding)
@@ -150,14 +158,18 @@ __global__ void __launch_bounds__(256) k_gmg_flags(Grid gc, Grid gf, const float
     }
 }
 
-// rows of a level: per active block, component-major
+// ---- row list of an explicit level, k-plane major ---------------------------------------------------------------
+// tile = one k-plane of an 8x8x8 block (64 cells, two warps); tile id = plane * (nby * nbx) + bj * nbx + bi.
+// per_tile[tile] = unknowns in the tile (all three components); zero for tiles of inactive blocks (memset by the host).
 __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_counts(Grid g, const int *__restrict__ list, const int *__restrict__ count,
-                                                                const float *__restrict__ diag, int *__restrict__ per_block) {
+                                                                const float *__restrict__ diag, int *__restrict__ per_tile) {
     __shared__ int wsum[CG_THREADS / 32];
     int nb = *count;
     size_t T = (size_t)g.total;
+    const int tpp = g.nbx * g.nby;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        const int blk = list[b];
+        BlockCell c = block_cell(g, blk, threadIdx.x);
         int n = 0;
         if (c.inside) {
             int id = gidx(g, c.i, c.j, c.k);
@@ -167,33 +179,34 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_counts(Grid g, const int
         __syncthreads();
         if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < CG_THREADS / 32; w++) t += wsum[w];
-            per_block[b] = t;
+        if (threadIdx.x < 8) {   // thread p: plane p of the block = warps 2p, 2p+1
+            int bk = blk / tpp, rest = blk - bk * tpp;
+            per_tile[(bk * FLIP_B + threadIdx.x) * tpp + rest] = wsum[2 * threadIdx.x] + wsum[2 * threadIdx.x + 1];
         }
     }
 }
 
 __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *__restrict__ list, const int *__restrict__ count,
-                                                              const float *__restrict__ diag, const int *__restrict__ offset,
+                                                              const float *__restrict__ diag, const int *__restrict__ tile_off,
                                                               int *__restrict__ rows, int *__restrict__ rowmap) {
     __shared__ int wsum[CG_THREADS / 32];
     int nb = *count;
     size_t T = (size_t)g.total;
+    const int tpp = g.nbx * g.nby;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        BlockCell c = block_cell(g, list[b], threadIdx.x);
+        const int blk = list[b];
+        BlockCell c = block_cell(g, blk, threadIdx.x);
         int id = c.inside ? gidx(g, c.i, c.j, c.k) : 0;
-        int base = offset[b];
+        const int bk = blk / tpp, rest = blk - bk * tpp;
+        int base = tile_off[(bk * FLIP_B + (wid >> 1)) * tpp + rest];   // first row of this thread's plane tile
         for (int m = 0; m < 3; m++) {
             bool has = c.inside && diag[m * T + id] != 0.0f;
             unsigned bal = __ballot_sync(0xffffffffu, has);
             __syncthreads();
             if (lane == 0) wsum[wid] = __popc(bal);
             __syncthreads();
-            int before = 0, total = 0;
-            for (int w = 0; w < CG_THREADS / 32; w++) { if (w < wid) before += wsum[w]; total += wsum[w]; }
+            const int before = (wid & 1) ? wsum[wid - 1] : 0, total = wsum[wid & ~1] + wsum[wid | 1];
             if (has) {
                 int r = base + before + __popc(bal & ((1u << lane) - 1u));
                 rows[r] = (int)(m * T + id);
@@ -202,6 +215,22 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *
             base += total;
         }
     }
+}
+
+// row ranges of a level: rng[0..1] = this rank's slab of planes (cuts of `level`, or everything when cuts == null),
+// rng[2..3] = all rows
+__global__ void k_gmg_ranges(const int *__restrict__ tile_off, int ntiles, int tpp, const Cuts *__restrict__ cuts, int level, int rank,
+                             int *__restrict__ rng, int *__restrict__ nrows) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = tile_off[ntiles];
+    int a = 0, b = n;
+    if (cuts) {
+        int t0 = cuts->c[level][rank] * tpp, t1 = cuts->c[level][rank + 1] * tpp;
+        a = tile_off[t0 < ntiles ? t0 : ntiles];
+        b = tile_off[t1 < ntiles ? t1 : ntiles];
+    }
+    rng[0] = a; rng[1] = b; rng[2] = 0; rng[3] = n;
+    *nrows = n;
 }
 
 // pn: prolongation normaliser of every unknown of the fine level
@@ -254,7 +283,7 @@ FLIP_D int gmg_entries_l0(int m, int mp, int id, int sy, int sz, size_t T, const
 // size ~1e4 that cancel.  FINE0: the fine level is level 0 (matrix-free coefficients), else an explicit level.
 #define GMG_BUILD_WARPS 8
 template <bool FINE0>
-__global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, int nrows_c,
+__global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Grid gf, const int *__restrict__ rows_c, const int *__restrict__ rng,
                                                                      const float *__restrict__ diag_c, float *__restrict__ S_c,
                                                                      const float *__restrict__ diag_f, const float *__restrict__ pn_f,
                                                                      const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
@@ -264,9 +293,9 @@ __global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Gri
     __shared__ int sslot_s[GMG_BUILD_WARPS][256];
     __shared__ double sval_s[GMG_BUILD_WARPS][256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int task = blockIdx.x * GMG_BUILD_WARPS + wid;        // (row, mp), mp fastest
-    if (task >= 3 * nrows_c) return;                            // whole warp leaves together; no block-wide barrier below
-    const int r = task / 3, mp = task - 3 * r;
+    const int task = blockIdx.x * GMG_BUILD_WARPS + wid;        // (row of this rank's range, mp), mp fastest
+    const int r = rng[0] + task / 3, mp = task % 3;
+    if (r >= rng[1]) return;                                    // whole warp leaves together; no block-wide barrier below
     // A_c is symmetric: the blocks below the diagonal (row component > column component) are mirrored from the ones
     // above it by k_gmg_mirror instead of being computed a second time (a third of the tasks)
     if (rows_c[r] / gc.total > mp) return;
@@ -463,14 +492,15 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
                                                     const CGState *__restrict__ st) {
     __shared__ int offs[3][GMG_STRIDE];
     if (st && st->done) return;
+    if (!xch_enter(L.X)) return;
     if (MODE != 0) {
         for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
         __syncthreads();
     }
-    const int nrows = *L.nrows;
+    const int r0 = L.rng[0], r1 = L.rng[1];
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+    for (int r = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < r1; r += nwarps) {
         int enc = L.rows[r];
         int m = enc / L.g.total, id = enc - m * L.g.total;
         if (MODE == 0) {
@@ -491,6 +521,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
             else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
         }
     }
+    xch_leave(L.X, false);
 }
 
 // ---- level 0 on the solver's compact cell list ------------------------------------------------
@@ -503,6 +534,7 @@ struct G0Params {
     const int *cell_list, *cell_count;
     const float *coef, *diag, *pn;
     const float *vol;     // the solver's 7 volume grids (vvol); faces U,V,W are grids 1,2,3
+    Xch X;                // exchange context (the cell list holds this rank's slab only)
 };
 
 template <int MODE>
@@ -510,6 +542,7 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
                                                      float *__restrict__ out, double *__restrict__ zout, float omega,
                                                      const CGState *__restrict__ st) {
     if (st && st->done) return;
+    if (MODE != 0 && !xch_enter(L.X)) return;   // mode 0 reads and writes this rank's own cells only
     const Grid &g = L.g;
     const int sy = SY(g), sz = SZ(g);
     const size_t T = (size_t)g.total;
@@ -569,6 +602,7 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
             }
         }
     }
+    if (MODE != 0) xch_leave(L.X, false);
 }
 
 // value of the coarse correction P x_c at fine face (m; i,j,k), not yet divided by pn
@@ -596,6 +630,7 @@ FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float 
 __global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const float *__restrict__ xc, float *__restrict__ xf,
                                                        const CGState *__restrict__ st) {
     if (st && st->done) return;
+    if (!xch_enter(F.X)) return;
     const Grid &g = F.g;
     const size_t T = (size_t)g.total;
     const int nc = *F.cell_count;
@@ -608,14 +643,15 @@ __global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const
             if (p > 0.0f) xf[m * T + id] += gmg_interp(m, i, j, k, gc, xc) / p;
         }
     }
+    xch_leave(F.X, false);
 }
 
 // explicit levels: x += P x_c, one thread per fine row
 __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *__restrict__ pn, Grid gc, const float *__restrict__ xc,
                                                       float *__restrict__ xf, const CGState *__restrict__ st) {
     if (st && st->done) return;
-    const int nrows = *F.nrows;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int r0 = F.rng[0], r1 = F.rng[1];
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
         int enc = F.rows[r];
         int m = enc / F.g.total, id = enc - m * F.g.total;
         float p = pn[enc];
@@ -632,10 +668,11 @@ __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *_
 __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
                                                              float *__restrict__ x0, const CGState *__restrict__ st) {
     if (st && st->done) return;
-    const int nrows = *C.nrows;
+    if (!xch_enter(C.X)) return;
+    const int r0 = C.rng[0], r1 = C.rng[1];
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+    for (int r = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < r1; r += nwarps) {
         int enc = C.rows[r];
         int m = enc / C.g.total, id = enc - m * C.g.total;
         int I, J, K;
@@ -661,6 +698,7 @@ __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf
             x0[enc] = C.wj[r] * bv;
         }
     }
+    xch_leave(C.X, false);
 }
 
 // ---- coarsest level: dense inverse -------------------------------------------------------------

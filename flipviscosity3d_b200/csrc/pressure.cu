@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) k_pressure_build(Grid g, const float *__r
 __global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const float4 *__restrict__ coef, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     if (P.st[parity].done) return;
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     const int sy = SY(g), sz = SZ(g);
     const double *__restrict__ s = P.s;
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const
         sq += sc * val;
     }
     sq = cta_reduce<false>(sq, sm);
-    if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
+    if (threadIdx.x == 0) PART_STORE(P, 0, sq);
+    xch_leave(P.X, true);
 }
 
 __global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const double *__restrict__ x, float *__restrict__ pr) {
@@ -105,21 +107,10 @@ __global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const 
 
 void solve_pressure(Sim &s, float dt) {
     const Grid &g = s.g;
-    // decompose only when the solve is big enough to pay for its exchanges (sim.h, dist_min_unknowns); the size of the
-    // previous solve decides, so that every rank takes the same branch
-    const bool replicate = s.nranks > 1 && (long long)s.pres_last_unknowns < s.dist_min_unknowns * s.nranks;
-    const int mode = s.nranks > 1 ? (replicate ? 1 : 0) : -1;
-#ifndef FLIP_CPU_EMU
-    if (mode != s.pres_last_mode && s.cg_graph[0]) {
-        cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[0]);
-        s.cg_graph[0] = nullptr;
-    }
-#endif
-    s.pres_last_mode = mode;
-    ReplicatedGuard replicated(s, replicate);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
+    xch_update_cuts(s);   // k-slabs balanced by liquid cells (no-op on one GPU)
     // scale = deltaTime / (dx*dx) in double, used as (float)scale (src/pressuresolver.cpp:250, 259)
     double scale = (double)dt / (g.dxd * g.dxd);
     long long nf = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
@@ -130,35 +121,38 @@ void solve_pressure(Sim &s, float dt) {
     build_block_list<1>(s, diag);
     // the search direction is read with a one-cell halo: it must be zero outside the active blocks
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * (size_t)g.total, s.stream));
-    CGParams P;
-    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
-    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
-    P.part = s.part; P.st = s.cgst; P.strict = 1; P.flexible = 0;
+    CGParams P = cg_params(s, 1);
     int G = cg_grid(s);
     const float4 *coef = s.pcoef;
     cudaStream_t st = s.stream;
     int pmaxit = s.pressure_maxit * s.pressure_maxit_scale;
     CGState h;
+    // phase A of an iteration: one ghost plane of the search direction each way, then the 7-point stencil
+    auto apply_on = [&](CGParams &Q) {
+        return [&s, &Q, G, st, coef](int parity) {
+            xch_push_halo(s, s.g, Q.s, sizeof(double), 1, 0, 1);
+            FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, Q, coef, parity);
+            s.kernel_launches++;
+        };
+    };
     if (s.cg_variant_pressure == 1) {
         // the search direction of the stencil kernel is u = M^-1 r here: it needs the zero halo too
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * (size_t)g.total, s.stream));
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
-        h = run_cg2<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, [&](int parity) {
-            FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, Pu, coef, parity);
-        }, 0);
+        h = run_cg2<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, apply_on(Pu), 0);
     } else {
-        h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, [&](int parity) {
-            dist_halo_exchange(s, P.s, 1);   // one ghost plane of the search direction per stencil apply
-            FLIP_LAUNCH_SYNC(k_pressure_apply, G, CG_THREADS, st, P, coef, parity);
-        }, 0);
+        h = run_cg<1>(s, P, diag, s.pressure_tol, 0.0, pmaxit, apply_on(P), 0);
     }
-    dist_allgather_slabs(s, s.cg_x, 1);
+    // every rank gets every slab of the solution
+    xch_push_gather(s, g, s.cg_x, sizeof(double), 1, 0);
+    xch_barrier(s);
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    xch_check(s);
     long long nc = (long long)g.ni * g.nj * g.nk;
     FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);
     s.kernel_launches++;
     KERNEL_CHECK();
-    if (dist_p2p_status(s) != 0) throw FlipError("multi-GPU peer-memory exchange timed out (a rank is missing or out of step)");
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
@@ -168,7 +162,6 @@ void solve_pressure(Sim &s, float dt) {
     s.pres_stats.iters = h.iter; s.pres_stats.converged = h.converged; s.pres_stats.resid = h.resid;
     s.pres_stats.bmax = h.bmax; s.pres_stats.skipped = (h.iter == 0 && h.converged) ? 1 : 0;
     s.pres_stats.blocks = s.count_host[0]; s.pres_stats.unknowns = s.count_host[1];
-    s.pres_last_unknowns = s.count_host[1];
     s.pres_stats.ms = ms;
     if (s.verbose) {
         printf("\tpressure: %d iterations, max|r| %.3e, %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,

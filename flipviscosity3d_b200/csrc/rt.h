@@ -8,12 +8,16 @@
     emu::launch((unsigned)(grid), (unsigned)(block), false, [&]() { kernel(__VA_ARGS__); })
 #define FLIP_LAUNCH_SYNC(kernel, grid, block, stream, ...) \
     emu::launch((unsigned)(grid), (unsigned)(block), true, [&]() { kernel(__VA_ARGS__); })
+#define FLIP_LAUNCH_X(sync, kernel, grid, block, stream, ...) \
+    emu::launch((unsigned)(grid), (unsigned)(block), (sync), [&]() { kernel(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
 // FLIP_LAUNCH: kernel without intra-block synchronisation; FLIP_LAUNCH_SYNC: kernel that uses
 // __syncthreads / warp shuffles (the distinction only matters to the CPU emulator).
 #define FLIP_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define FLIP_LAUNCH_SYNC(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// FLIP_LAUNCH_X: kernel whose only block-wide synchronisation is the multi-GPU hand-shake (xch.h); `sync` = handle is sharded
+#define FLIP_LAUNCH_X(sync, kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
 #include <cstdio>

@@ -1,6 +1,8 @@
 // Device-resident simulation state and the stage entry points (host side of the kernels).
 #pragma once
 #include "grid.h"
+#include "heap.h"
+#include "xch.h"
 #include <string>
 #include <vector>
 
@@ -70,9 +72,10 @@ struct Sim {
     int cg_variant_viscosity = 0;
     int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
     int verbose = 0;
-    int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph (1 GPU)
+    int use_graphs = 1;                 // replay the CG iteration chunk from a CUDA graph
     void *cg_graph[2] = {0, 0};         // cudaGraphExec_t: [0] pressure, [1] viscosity
-    int cg_graph_chunk[2] = {0, 0};
+    unsigned long long cg_graph_tag[2] = {0, 0};   // chunk, variant and exchange epoch the graph was captured under
+    long long cg_graph_launches[2] = {0, 0};
     bool viscosity_nonzero = true;      // reference initial viscosity is 1.0 everywhere
 
     // --- particles (SoA, cell-binned every substep) ---
@@ -118,23 +121,26 @@ struct Sim {
     int *blk_count = 0;       // [1]
     int *cell_list = 0;       // [total] compact list of cells with >= 1 unknown (this solve)
     int *cell_count = 0;      // [1]
-    double *part = 0;         // [4*FLIP_CG_MAXGRID] reduction partials
+    double *part = 0;         // [6 * FLIP_MAX_RANKS * FLIP_CG_MAXGRID] reduction partials (kind-major, cg.h)
     CGState *cgst = 0;        // [2] ping-pong
     CGState *cgst_host = 0;   // pinned
     int *count_host = 0;      // pinned [2]: active blocks, unknowns
     int *unk_count = 0;       // [1] device
 
-    // --- multi-GPU: 1-D slab decomposition of the solver blocks along k (dist.cu) ---
+    // --- multi-GPU (dist.cu, xch.h): replicated state in a symmetric heap, work cut into k-slabs, results delivered by
+    // peer-memory stores.  `sharded` is set once every rank's heap is mapped (flip_dist_p2p_import); until then several
+    // ranks are plain replicas.
+    SymHeap heap;
     int rank = 0, nranks = 1;
-    void *nccl = 0;           // ncclComm_t
-    void *p2p = 0;            // P2PState* (p2p.cu): peer-memory mailboxes for the per-iteration exchanges
-    int bz0 = 0, bz1 = 0;     // owned range of 8-cell block layers in k: [bz0, bz1)
-    // A CG solve is decomposed only when it is big enough to pay for its per-iteration exchanges (two latency-bound
-    // peer-memory round trips, ~25 us): below this many unknowns per rank every rank runs the whole solve.
-    // Measured at 256^3 on 2 GPUs: 0.62 M pressure unknowns, 9.3 ms replicated vs 18.5 ms decomposed.
-    long long dist_min_unknowns = 1000000;
-    int pres_last_unknowns = 0;   // of the previous pressure solve (identical on every rank)
-    int pres_last_mode = -1;      // 0 decomposed, 1 replicated: a flip invalidates the captured CG graph
+    void *nccl = 0;           // ncclComm_t (rendezvous / barrier only: nothing on the substep path calls NCCL)
+    bool sharded = false;
+    Link *link = 0;           // this rank's hand-shake counters (in the heap: peers store into it)
+    Link **link_peers = 0;    // device table [FLIP_MAX_RANKS]
+    Cuts *cuts = 0;           // slab cuts of the current substep (device)
+    int *plane_count = 0;     // [nk + 1] liquid cells per k-plane
+    double **part_peers = 0;  // device table [FLIP_MAX_RANKS]: `part` of every rank
+    unsigned long long xch_epoch = 1;   // bumped whenever the exchange set-up changes: captured graphs are keyed by it
+    double xch_timeout_s = 20.0;        // a rank that waits longer than this for its peers gives up (Link::status)
 
     void *user_ev[4] = {0, 0, 0, 0};   // cudaEvent_t slots of flip_event_record (device-side timing for callers)
 
@@ -148,17 +154,14 @@ struct Sim {
     float *vc(int c) { return vel + (size_t)c * g.total; }
 };
 
-// A solve that every rank runs in full on its own copy of the (bit-identical) state, without exchanges: the handle
-// looks like a single-rank one for the duration of the guard.
-struct ReplicatedGuard {
-    Sim &s; int nranks, bz0, bz1;
-    ReplicatedGuard(Sim &sim, bool on) : s(sim), nranks(sim.nranks), bz0(sim.bz0), bz1(sim.bz1) {
-        if (on) { s.nranks = 1; s.bz0 = 0; s.bz1 = s.g.nbz; }
-    }
-    ~ReplicatedGuard() { s.nranks = nranks; s.bz0 = bz0; s.bz1 = bz1; }
-};
-
 // api.cu
+template <class T>
+static inline void heap_alloc(Sim &s, T *&p, size_t n) {   // zero-filled
+    p = (T *)s.heap.alloc(n * sizeof(T));
+    CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), s.stream));
+}
+template <class T>
+static inline void heap_free(Sim &s, T *&p) { if (p) s.heap.release(p); p = nullptr; }
 void sim_alloc(Sim &s, int ni, int nj, int nk, float dx);
 void sim_free(Sim &s);
 void sim_reserve_particles(Sim &s, long long n);
@@ -186,26 +189,23 @@ void viscosity_free(Sim &s);
 int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_launch, unsigned long long *alg_bytes);
 
 // dist.cu
-void dist_setup_slab(Sim &s);
 void dist_init(Sim &s, int rank, int nranks, const void *unique_id);
 void dist_shutdown(Sim &s);
 void dist_get_unique_id(void *out128);
-void dist_reduce_partials(Sim &s, double *part, int n, bool is_max);   // collapse n partials + allreduce
-void dist_halo_exchange(Sim &s, double *field, int ncomp);            // one ghost plane each side of the slab
-void dist_allgather_slabs(Sim &s, double *field, int ncomp);          // every rank gets every slab
-void dist_allreduce_int(Sim &s, int *dev_value);
-// p2p.cu
 int dist_p2p_blob_size();
 void dist_p2p_export(Sim &s, void *out);
 void dist_p2p_import(Sim &s, const void *all_blobs);
 void dist_p2p_shutdown(Sim &s);
-bool dist_p2p_active(Sim &s);
-int dist_p2p_status(Sim &s);
-void dist_p2p_reduce(Sim &s, double *part, int n, bool is_max);
-void dist_p2p_halo(Sim &s, double *field, int ncomp);
-void dist_p2p_step(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp);
-// sum partials + max partials (+ optional halo of `field`) in one exchange where peer memory is active
-void dist_reduce_pair(Sim &s, double *part_sum, double *part_max, int n, double *field, int ncomp);
+// exchange helpers; every one is a no-op unless the handle is sharded
+Xch xch_of(Sim &s);                          // what the kernels take (nranks == 1 when not sharded)
+const Cuts *xch_cuts(Sim &s);                // device cuts, or null when not sharded
+int xch_rank(Sim &s);
+void xch_update_cuts(Sim &s);                // balanced k-slabs from the current liquid SDF
+void xch_push_halo(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level, int halo);   // ghost planes -> k-neighbours
+void xch_push_gather(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level);           // whole slab -> every rank
+void xch_push_rows(Sim &s, const int *rng_dev, void *base, size_t row_bytes);                          // row range -> every rank
+void xch_barrier(Sim &s);                    // everything pushed so far has arrived everywhere
+void xch_check(Sim &s);                      // throws if a hand-shake timed out
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
                                                            const float *__restrict__ vdiag, const float *__restrict__ vvol, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     if (P.st[parity].done) return;
+    if (!xch_enter(P.X)) return;
     const Grid &g = P.g;
     const int sy = SY(g), sz = SZ(g);
     const size_t T = (size_t)g.total;
@@ -314,14 +315,8 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
         }
     }
     sq = cta_reduce<false>(sq, sm);
-    if (threadIdx.x == 0) P.part[blockIdx.x] = sq;
-}
-
-
-template <class T>
-static void vmg_dev_alloc(T *&p, size_t n) {
-    CUDA_CHECK(cudaMalloc((void **)&p, n * sizeof(T)));
-    CUDA_CHECK(cudaMemset(p, 0, n * sizeof(T)));
+    if (threadIdx.x == 0) PART_STORE(P, 0, sq);
+    xch_leave(P.X, true);
 }
 
 static void gmg_free(Sim &s);
@@ -335,30 +330,35 @@ static GMG *gmg_get(Sim &s) {
     GMG *M = new GMG();
     s.gmg = M;
     CUDA_CHECK(cudaMallocHost((void **)&M->count_host, 4 * sizeof(int)));
-    vmg_dev_alloc(M->dense, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
-    vmg_dev_alloc(M->Ainv, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
+    heap_alloc(s, M->dense, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
+    heap_alloc(s, M->Ainv, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
     Grid g = s.g;
     for (int l = 0; l < GMG_MAX_LEVELS; l++) {
         GLevel &L = M->lv[l];
         L.g = g;
         size_t T = (size_t)g.total;
-        vmg_dev_alloc(L.x[0], 3 * T);
-        vmg_dev_alloc(L.x[1], 3 * T);
-        vmg_dev_alloc(L.r, 3 * T);
-        vmg_dev_alloc(L.pn, 3 * T);
+        heap_alloc(s, L.x[0], 3 * T);
+        heap_alloc(s, L.x[1], 3 * T);
+        heap_alloc(s, L.r, 3 * T);
+        heap_alloc(s, L.pn, 3 * T);
+        heap_alloc(s, L.rng, 4);
         if (l == 0) {
             L.diag = s.vdiag; L.blk_flag = s.blk_flag; L.blk_list = s.blk_list; L.blk_count = s.blk_count;
             L.owns = false;
         } else {
-            vmg_dev_alloc(L.diag, 3 * T); vmg_dev_alloc(L.b, 3 * T);
-            vmg_dev_alloc(L.blk_flag, (size_t)g.nblocks); vmg_dev_alloc(L.blk_list, (size_t)g.nblocks);
-            vmg_dev_alloc(L.blk_count, 1);
-            vmg_dev_alloc(L.rows, 3 * T); vmg_dev_alloc(L.rowmap, 3 * T); vmg_dev_alloc(L.nrows_dev, 1);
-            vmg_dev_alloc(L.offs, 3 * GMG_STRIDE);
+            heap_alloc(s, L.diag, 3 * T); heap_alloc(s, L.b, 3 * T);
+            heap_alloc(s, L.blk_flag, (size_t)g.nblocks); heap_alloc(s, L.blk_list, (size_t)g.nblocks);
+            heap_alloc(s, L.blk_count, 1);
+            heap_alloc(s, L.rows, 3 * T); heap_alloc(s, L.rowmap, 3 * T); heap_alloc(s, L.nrows_dev, 1);
+            L.ntiles = FLIP_B * g.nbz * g.nby * g.nbx;
+            heap_alloc(s, L.tile_off, (size_t)L.ntiles + 1);
+            heap_alloc(s, L.scan_tmp, (size_t)L.ntiles / 2048 + 2);
+            heap_alloc(s, L.offs, 3 * GMG_STRIDE);
             std::vector<int> offs(3 * GMG_STRIDE, 0);
             for (int m = 0; m < 3; m++)
                 for (int slot = 0; slot < GMG_SLOTS; slot++) offs[m * GMG_STRIDE + slot] = gmg_slot_offset(g, m, slot);
-            CUDA_CHECK(cudaMemcpy(L.offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpyAsync(L.offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+            CUDA_CHECK(cudaStreamSynchronize(s.stream));
             L.owns = true;
         }
         M->nalloc = l + 1;
@@ -373,16 +373,8 @@ static GMG *gmg_get(Sim &s) {
 static void gmg_free(Sim &s) {
     GMG *M = (GMG *)s.gmg;
     if (!M) return;
-    for (int l = 0; l < M->nalloc; l++) {
-        GLevel &L = M->lv[l];
-        cudaFree(L.x[0]); cudaFree(L.x[1]); cudaFree(L.r); cudaFree(L.pn);
-        if (L.owns) {
-            cudaFree(L.diag); cudaFree(L.b); cudaFree(L.blk_flag); cudaFree(L.blk_list); cudaFree(L.blk_count);
-            cudaFree(L.rows); cudaFree(L.rowmap); cudaFree(L.nrows_dev); cudaFree(L.S); cudaFree(L.wj); cudaFree(L.offs);
-        }
-    }
+    // the buffers live in the handle's heap, which is released as a whole (sim_free)
     cudaFreeHost(M->count_host);
-    cudaFree(M->dense); cudaFree(M->Ainv);
 #ifndef FLIP_CPU_EMU
     if (M->exec) cudaGraphExecDestroy((cudaGraphExec_t)M->exec);
 #endif
@@ -390,9 +382,13 @@ static void gmg_free(Sim &s) {
     s.gmg = nullptr;
 }
 
-static GLevelDev gmg_dev(const GLevel &L) {
+// device view of a level; `own`: restricted to this rank's slab of rows and hand-shaking with the other ranks
+static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
     GLevelDev d;
     d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
+    d.rng = own ? L.rng : L.rng + 2;
+    d.X = xch_of(s);
+    if (!own) d.X.nranks = 1;
     return d;
 }
 static int gmg_grid(const Sim &s, const GLevel &L) {
@@ -406,6 +402,12 @@ static int gmg_row_grid(const Sim &s, const GLevel &L) {
     return (int)(G < 1 ? 1 : (G > cap ? cap : G));
 }
 
+// Levels whose rows are cut into k-slabs when the handle is sharded: the sweeps of level 1 and the Galerkin products and
+// restrictions of levels 1 and 2 (their cuts are whole planes, xch.h).  Deeper levels are small and latency bound: every
+// rank runs them in full on its own copy.
+#define GMG_SHARD_SWEEP_LEVELS 1
+#define GMG_SHARD_BUILD_LEVELS 2
+
 // Galerkin operators for this solve: unknown flags, row lists, transfer normalisers, A_c = P^T A P / 8
 static void gmg_build(Sim &s, GMG &M) {
     M.pre = s.mg_sweeps < 1 ? 1 : s.mg_sweeps;
@@ -417,6 +419,7 @@ static void gmg_build(Sim &s, GMG &M) {
     int want = s.mg_levels < M.nalloc ? (s.mg_levels < 1 ? 1 : s.mg_levels) : M.nalloc;
     M.nlevels = 1;
     M.dense_last = false;
+    const Cuts *cuts = xch_cuts(s);
     for (int l = 0; l < want; l++) {
         GLevel &L = M.lv[l];
         size_t T = (size_t)L.g.total;
@@ -427,53 +430,62 @@ static void gmg_build(Sim &s, GMG &M) {
         CUDA_CHECK(cudaMemsetAsync(L.pn, 0, 3 * T * sizeof(float), s.stream));
         if (l == 0) continue;
         GLevel &F = M.lv[l - 1];
+        const bool shard = cuts && l <= GMG_SHARD_BUILD_LEVELS;
         CUDA_CHECK(cudaMemsetAsync(L.b, 0, 3 * T * sizeof(float), s.stream));
         CUDA_CHECK(cudaMemsetAsync(L.rowmap, 0xFF, 3 * T * sizeof(int), s.stream));
+        CUDA_CHECK(cudaMemsetAsync(L.tile_off, 0, ((size_t)L.ntiles + 1) * sizeof(int), s.stream));
         long long n = (long long)(L.g.ni + 1) * (L.g.nj + 1) * (L.g.nk + 1);
         FLIP_LAUNCH(k_gmg_flags, cdiv(n, 256), 256, s.stream, L.g, F.g, (const float *)F.diag, L.diag);
         DiagViscosity d{L.diag, L.g.total};
         build_block_list_on<3>(s, L.g, d, L.blk_flag, L.blk_list, L.blk_count);
         int G = gmg_grid(s, L);
         FLIP_LAUNCH_SYNC(k_gmg_row_counts, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
-                         (const float *)L.diag, L.blk_flag);
-        FLIP_LAUNCH_SYNC(k_scan_small, 1, 1024, s.stream, L.blk_flag, (const int *)L.blk_count, L.nrows_dev);
+                         (const float *)L.diag, L.tile_off);
+        exclusive_scan(s, L.tile_off, L.tile_off, L.scan_tmp, L.ntiles);
         FLIP_LAUNCH_SYNC(k_gmg_row_fill, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
-                         (const float *)L.diag, (const int *)L.blk_flag, L.rows, L.rowmap);
+                         (const float *)L.diag, (const int *)L.tile_off, L.rows, L.rowmap);
+        FLIP_LAUNCH(k_gmg_ranges, 1, 32, s.stream, (const int *)L.tile_off, L.ntiles, L.g.nbx * L.g.nby,
+                    l < XCH_LEVELS ? cuts : (const Cuts *)nullptr, l, xch_rank(s), L.rng, L.nrows_dev);
         s.kernel_launches += 4;
         CUDA_CHECK(cudaMemcpyAsync(M.count_host, L.nrows_dev, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         L.nrows = M.count_host[0];
         if (L.nrows == 0) break;
         if ((size_t)L.nrows > L.cap) {
-            if (L.S) { CUDA_CHECK(cudaFree(L.S)); CUDA_CHECK(cudaFree(L.wj)); }
+            heap_free(s, L.S); heap_free(s, L.wj);
             L.cap = (size_t)L.nrows + (size_t)L.nrows / 4 + 1024;
-            CUDA_CHECK(cudaMalloc((void **)&L.S, L.cap * GMG_STRIDE * sizeof(float)));
-            CUDA_CHECK(cudaMemsetAsync(L.S, 0, L.cap * GMG_STRIDE * sizeof(float), s.stream));   // padding slots stay 0
-            CUDA_CHECK(cudaMalloc((void **)&L.wj, L.cap * sizeof(float)));
+            heap_alloc(s, L.S, L.cap * GMG_STRIDE);   // zero filled: padding slots stay 0
+            heap_alloc(s, L.wj, L.cap);
         }
         // transfer normaliser of the fine level, then the Galerkin product
         FLIP_LAUNCH(k_gmg_pnorm, gmg_grid(s, F), CG_THREADS, s.stream, F.g, (const int *)F.blk_list, (const int *)F.blk_count,
                     (const float *)F.diag, L.g, (const float *)L.diag, F.pn);
         int GB = cdiv(3LL * L.nrows, GMG_BUILD_WARPS);
+        const int *rng = shard ? L.rng : L.rng + 2;
         if (l == 1) {
             auto kb = &k_gmg_build<true>;
-            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, rng, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)s.vcoef, (const int *)nullptr,
                         (const float *)s.vvol, 0);
         } else {
             auto kb = &k_gmg_build<false>;
-            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, L.nrows, (const float *)L.diag, L.S,
+            FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, rng, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)nullptr, (const int *)F.rowmap,
                         (const float *)F.S, F.nrows);
         }
+        if (shard) {
+            // every rank computed the rows of its own slab: deliver them to everybody (the next level's products and the
+            // mirror pass read rows of any slab), then make sure everybody's rows have arrived
+            xch_push_rows(s, L.rng, L.S, GMG_STRIDE * sizeof(float));
+            xch_barrier(s);
+        }
         FLIP_LAUNCH(k_gmg_mirror, cdiv(160LL * L.nrows, 256), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const int *)L.rowmap, L.S);
-        s.kernel_launches++;
         FLIP_LAUNCH_SYNC(k_gmg_diag, cdiv(L.nrows, 8), 256, s.stream, L.g, (const int *)L.rows, L.nrows, (const float *)L.S, L.diag, L.wj, M.omega);
-        s.kernel_launches += 3;
+        s.kernel_launches += 4;
         M.nlevels = l + 1;
         if (s.mg_dense && L.nrows <= (s.mg_dense_rows < GMG_DENSE_MAX ? s.mg_dense_rows : GMG_DENSE_MAX)) {
             // small enough for an exact solve: this is the last level
-            GLevelDev D = gmg_dev(L);
+            GLevelDev D = gmg_dev(s, L, false);
             FLIP_LAUNCH_SYNC(k_gmg_dense_inverse, 1, 1024, s.stream, D, (const int *)L.rowmap, M.dense, M.Ainv);
             s.kernel_launches++;
             M.dense_last = true;
@@ -484,44 +496,64 @@ static void gmg_build(Sim &s, GMG &M) {
 }
 
 // z = Vcycle(r): r is the CG residual (fp64) on level 0.  All grid sizes depend only on what the host
-// knows after gmg_build (row counts), every other argument is a pointer into the hierarchy, so the whole
-// launch sequence can be captured into a CUDA graph once per solve.
+// knows after gmg_build (row capacities), every other argument is a pointer into the hierarchy, so the whole
+// launch sequence can be captured into a CUDA graph.  On a sharded handle levels 0 and 1 work on this rank's slab:
+// every sweep is followed by a push of the ghost planes its successor reads (1 plane of level 0, 2 planes of level 1
+// - the Galerkin window); the restriction to level 2 is cut by rows and gathered, deeper levels run replicated.
 static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const CGState *st) {
     const float w = M.omega;
     int cur[GMG_MAX_LEVELS];
     auto l0_first = &k_gmg0_sweep<0>; auto l0_smooth = &k_gmg0_sweep<1>; auto l0_resid = &k_gmg0_sweep<2>; auto l0_last = &k_gmg0_sweep<3>;
     auto sweep1 = &k_gmg_sweep<1>; auto sweep2 = &k_gmg_sweep<2>;
     const int last = M.nlevels - 1;
+    const bool sh = xch_cuts(s) != nullptr;
     GLevel &L0 = M.lv[0];
     G0Params P0;
     P0.g = L0.g; P0.cell_list = s.cell_list; P0.cell_count = s.cell_count; P0.coef = s.vcoef; P0.diag = L0.diag; P0.pn = L0.pn; P0.vol = s.vvol;
+    P0.X = xch_of(s);
     const int G0 = s.num_sms * 8;
     const float *nof = nullptr;
+    auto halo0 = [&](float *x) { xch_push_halo(s, L0.g, x, sizeof(float), 3, 0, 1); };
     // level 0, downstroke
     FLIP_LAUNCH(l0_first, G0, 256, s.stream, P0, r_in, nof, L0.x[0], (double *)nullptr, w, st);
     cur[0] = 0;
+    halo0(L0.x[0]);
     if (last == 0) {
         for (int k = 1; k < 2 * M.pre_l[0] - 1; k++) {
-            FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+            FLIP_LAUNCH_X(sh, l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
             cur[0] ^= 1;
+            halo0(L0.x[cur[0]]);
         }
-        FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
+        FLIP_LAUNCH_X(sh, l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
         s.kernel_launches += 2 * M.pre_l[0];
         return;
     }
     for (int k = 1; k < M.pre_l[0]; k++) {
-        FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+        FLIP_LAUNCH_X(sh, l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
         cur[0] ^= 1;
+        halo0(L0.x[cur[0]]);
     }
-    FLIP_LAUNCH(l0_resid, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.r, (double *)nullptr, w, st);
+    FLIP_LAUNCH_X(sh, l0_resid, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.r, (double *)nullptr, w, st);
+    if (sh) xch_push_halo(s, L0.g, L0.r, sizeof(float), 3, 0, 2);
     s.kernel_launches += M.pre_l[0] + 1;
     // explicit levels, downstroke
     for (int l = 1; l <= last; l++) {
         GLevel &L = M.lv[l];
-        GLevelDev D = gmg_dev(L);
+        // sweeps on this rank's rows only (never the dense last level: its solve needs the whole right-hand side)
+        const bool own = sh && l <= GMG_SHARD_SWEEP_LEVELS && !(l == last && M.dense_last);
+        // the restriction INTO level l is cut by rows while level l-1 is (the rows' children live in this rank's slab)
+        const bool own_restrict = sh && l <= GMG_SHARD_SWEEP_LEVELS + 1 && l < XCH_LEVELS;
+        GLevelDev D = gmg_dev(s, L, own), Dr = gmg_dev(s, L, own_restrict);
         int GR = gmg_row_grid(s, L);
-        FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, D, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
+        FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
+        if (own) xch_push_halo(s, L.g, L.x[0], sizeof(float), 3, l, 2);
+        else if (own_restrict) {
+            // first replicated level: gather the restricted right-hand side and first iterate from all slabs
+            xch_push_gather(s, L.g, L.b, sizeof(float), 3, l);
+            xch_push_gather(s, L.g, L.x[0], sizeof(float), 3, l);
+            xch_barrier(s);
+        }
         if (l == last && M.dense_last) {
             FLIP_LAUNCH_SYNC(k_gmg_dense_apply, 8, 256, s.stream, D, (const float *)M.Ainv, (const float *)L.b, L.x[0], st);
             s.kernel_launches += 2;
@@ -531,34 +563,44 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         for (int k = 1; k < sweeps; k++) {
             FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
+            if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
-        if (l < last) FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
+        if (l < last) {
+            FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
+            if (own) xch_push_halo(s, L.g, L.r, sizeof(float), 3, l, 2);
+        }
         s.kernel_launches += sweeps + (l < last ? 1 : 0);
     }
     // upstroke
     for (int l = last - 1; l >= 1; l--) {
         GLevel &L = M.lv[l];
-        GLevelDev D = gmg_dev(L);
+        const bool own = sh && l <= GMG_SHARD_SWEEP_LEVELS;   // l < last here: never the dense level
+        GLevelDev D = gmg_dev(s, L, own);
         int GR = gmg_row_grid(s, L), GT = cdiv((long long)L.cap, 256) < s.num_sms * 8 ? cdiv((long long)L.cap, 256) : s.num_sms * 8;
+        // the coarser level is replicated (or, for a sharded one, its ghost planes were pushed after its last sweep)
         FLIP_LAUNCH(k_gmg_prolong, GT, 256, s.stream, D, (const float *)L.pn, M.lv[l + 1].g, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], st);
+        if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         for (int k = 0; k < M.pre_l[l]; k++) {
             FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
+            if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
         s.kernel_launches += 1 + M.pre_l[l];
     }
-    FLIP_LAUNCH(k_gmg0_prolong, G0, 256, s.stream, P0, M.lv[1].g, (const float *)M.lv[1].x[cur[1]], L0.x[cur[0]], st);
+    FLIP_LAUNCH_X(sh, k_gmg0_prolong, G0, 256, s.stream, P0, M.lv[1].g, (const float *)M.lv[1].x[cur[1]], L0.x[cur[0]], st);
+    halo0(L0.x[cur[0]]);
     for (int k = 0; k < M.pre_l[0] - 1; k++) {
-        FLIP_LAUNCH(l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
+        FLIP_LAUNCH_X(sh, l0_smooth, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.x[cur[0] ^ 1], (double *)nullptr, w, st);
         cur[0] ^= 1;
+        halo0(L0.x[cur[0]]);
     }
-    FLIP_LAUNCH(l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
+    FLIP_LAUNCH_X(sh, l0_last, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], (float *)nullptr, z_out, w, st);
     s.kernel_launches += 1 + M.pre_l[0];
 }
 
-// Multigrid-preconditioned CG: cg.h's run_cg_mg with the iteration chunk (stencil apply, update, V-cycle, dot,
-// direction: ~70 launches per iteration) replayed from a CUDA graph that is re-captured for every solve, because
-// row counts and (after a re-allocation) pointers of the hierarchy change from solve to solve.
+// Multigrid-preconditioned CG: the iteration chunk (stencil apply, update, V-cycle, dot, direction: ~70 launches per
+// iteration on one GPU, ~100 with the exchange pushes of a sharded handle) is replayed from a CUDA graph that is
+// re-captured only when a level is re-allocated, a parameter changes or the exchange set-up changes.
 template <class ApplyFn>
 static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double tol_rel, int maxit, ApplyFn apply,
                           const float *guess) {
@@ -600,20 +642,20 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
             gmg_vcycle(s, M, (const double *)P.r, P.z, (const CGState *)(P.st + parity));
             FLIP_LAUNCH_SYNC(kdot, G, CG_THREADS, s.stream, P, diag, parity);
             FLIP_LAUNCH_SYNC(kdir, G, CG_THREADS, s.stream, P, diag, parity);
-            s.kernel_launches += 4;
+            s.kernel_launches += 3;
         }
         per_chunk = s.kernel_launches - before;
     };
 #ifndef FLIP_CPU_EMU
     // The graph is keyed by everything the launch sequence depends on (level count, sweep counts, every pointer
-    // and capacity-derived grid size); row counts are read on the device.  It is re-captured only when a level
-    // was re-allocated or a parameter changed, typically once per simulation.
+    // and capacity-derived grid size, the exchange epoch); row counts and slab cuts are read on the device.
     cudaGraphExec_t exec = nullptr;
     if (s.use_graphs) {
         unsigned long long sig = 1469598103934665603ull;
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
         mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
+        mix(s.xch_epoch); mix((unsigned long long)s.sharded);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
             mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
@@ -672,12 +714,10 @@ void stage_apply_viscosity(Sim &s, float dt) {
     s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0, 0};
     if (!s.viscosity_nonzero) return;  // src/fluidsimulation.cpp:171-184
     const Grid &g = s.g;
-    // The multigrid hierarchy is not slab-decomposed yet: with several ranks every rank runs the whole
-    // (deterministic, hence bit-identical) multigrid solve instead of a slab of the 50x slower Jacobi-PCG.
-    ReplicatedGuard replicated(s, s.visc_precond == 2 && s.nranks > 1);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
+    xch_update_cuts(s);   // k-slabs of this substep, balanced by liquid cells (no-op on one GPU)
     viscosity_volumes(s);
     // factor = dt * invdx * invdx in float (src/viscositysolver.cpp:379-380)
     float invdx = 1.0f / g.dx;
@@ -690,37 +730,40 @@ void stage_apply_viscosity(Sim &s, float dt) {
     DiagViscosity diag{s.vdiag, g.total};
     build_block_list<3>(s, diag);
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
-    CGParams P;
-    P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
-    P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
-    P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
+    CGParams P = cg_params(s, 0);
     int G = cg_grid(s);
     const float *vcoef = s.vcoef, *vdiag = s.vdiag, *vvol = s.vvol;
     cudaStream_t st = s.stream;
     int maxit = s.visc_maxit * s.visc_maxit_scale;
     CGState h;
-    if (s.visc_precond == 2 && s.nranks == 1) {
+    // phase A of an iteration: ghost planes of the search direction (U, V and W: rows couple components at k +- 1),
+    // then the stencil
+    auto apply_on = [&](CGParams &Q) {
+        return [&s, &Q, G, st, vcoef, vdiag, vvol](int parity) {
+            xch_push_halo(s, s.g, Q.s, sizeof(double), 3, 0, 1);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Q, vcoef, vdiag, vvol, parity);
+            s.kernel_launches++;
+        };
+    };
+    if (s.visc_precond == 2) {
         GMG *M = gmg_get(s);
         gmg_build(s, *M);
         P.z = s.cg_z;
         P.flexible = s.mg_flexible;
-        h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit,
-                       [&](int parity) { FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity); },
-                       s.visc_warm_start ? (const float *)s.vel : nullptr);
+        h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit, apply_on(P), s.visc_warm_start ? (const float *)s.vel : nullptr);
     } else if (s.cg_variant_viscosity == 1) {
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
         CGParams Pu = P;
         Pu.s = s.cg_z; Pu.q = s.cg_w;
-        h = run_cg2<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Pu, vcoef, vdiag, vvol, parity);
-        }, 1);
+        h = run_cg2<3>(s, P, diag, 0.0, s.visc_tol, maxit, apply_on(Pu), 1);
     } else {
-        h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, [&](int parity) {
-            dist_halo_exchange(s, P.s, 3);   // U, V and W ghost planes: rows couple components at k +- 1
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, P, vcoef, vdiag, vvol, parity);
-        }, 1, s.visc_warm_start ? (const float *)s.vel : nullptr);
+        h = run_cg<3>(s, P, diag, 0.0, s.visc_tol, maxit, apply_on(P), 1, s.visc_warm_start ? (const float *)s.vel : nullptr);
     }
-    dist_allgather_slabs(s, s.cg_x, 3);
+    // every rank gets every slab of the solution
+    xch_push_gather(s, g, s.cg_x, sizeof(double), 3, 0);
+    xch_barrier(s);
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    xch_check(s);   // a broken exchange must not reach the velocity field
     // acceptance rule of src/viscositysolver.cpp:676-689
     bool accept = !h.fail && (h.converged || (h.iter >= maxit && h.resid < s.visc_accept));
     if (accept) {
@@ -728,7 +771,6 @@ void stage_apply_viscosity(Sim &s, float dt) {
         s.kernel_launches++;
     }
     KERNEL_CHECK();
-    if (dist_p2p_status(s) != 0) throw FlipError("multi-GPU peer-memory exchange timed out (a rank is missing or out of step)");
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaMemcpyAsync(s.count_host + 1, s.unk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
@@ -744,6 +786,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     }
 }
 
+// ---- debug access (tests / dev tools only) -------------------------------------------------------
 // y = A x for the viscosity system of the last solve, on raw padded fp64 arrays [3*total] (tests /
 // solver prototyping only).  Also: raw access to the row diagonals and face volumes.
 extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y_host) {
@@ -754,10 +797,9 @@ extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y
         CUDA_CHECK(cudaMemcpy(s.cg_z, x_host, n * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemsetAsync(s.cg_w, 0, n * sizeof(double), s.stream));
         CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
-        CGParams P;
-        P.g = g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
-        P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_z; P.q = s.cg_w; P.z = nullptr;
-        P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
+        CGParams P = cg_params(s, 0);
+        P.s = s.cg_z; P.q = s.cg_w;
+        P.X.nranks = 1;   // debug helper: whole field on this rank, no hand-shakes
         FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(y_host, s.cg_w, n * sizeof(double), cudaMemcpyDeviceToHost));
@@ -812,7 +854,7 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         GMG *M = (GMG *)s.gmg;
         if (!M || M->nlevels < 2 || M->lv[1].nrows == 0) return -1;
         GLevel &L = M->lv[1];
-        GLevelDev D = gmg_dev(L);
+        GLevelDev D = gmg_dev(s, L, false);
         auto sweep1 = &k_gmg_sweep<1>;
         int GR = gmg_row_grid(s, L);
         const float *nof = nullptr;
@@ -824,10 +866,8 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         *alg_bytes = (unsigned long long)L.nrows * (GMG_SLOTS + 5) * 4ull;
     } else if (n == "visc_apply") {
         if (s.visc_stats.unknowns == 0) return -1;
-        CGParams P;
-        P.g = s.g; P.blk_list = s.blk_list; P.blk_count = s.blk_count; P.cell_list = s.cell_list; P.cell_count = s.cell_count;
-        P.x = s.cg_x; P.r = s.cg_r; P.s = s.cg_s; P.q = s.cg_q; P.z = nullptr;
-        P.part = s.part; P.st = s.cgst; P.strict = 0; P.flexible = 0;
+        CGParams P = cg_params(s, 0);
+        P.X.nranks = 1;   // timing helper: this rank's cells, no hand-shakes
         CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
         int G = cg_grid(s);
         FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);

@@ -33,7 +33,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static
 
 struct dim3 {
@@ -80,7 +80,9 @@ struct State {
     unsigned ballot[64];
 };
 
-inline State &S() { static State s; return s; }
+inline State &S() { static thread_local State s; return s; }
+// ranks of a multi-rank test are host threads: their kernels hand-shake through __syncthreads-using helpers (xch.h)
+inline bool &force_sync() { static thread_local bool f = false; return f; }
 
 inline void yield() {
     State &s = S();
@@ -130,6 +132,7 @@ template <class F>
 void launch(unsigned grid, unsigned block, bool sync, F f) {
     State &s = S();
     s.gDim = dim3(grid); s.bDim = dim3(block);
+    if (force_sync()) sync = true;
     if (!sync) {
         s.fiberMode = false;
         for (unsigned b = 0; b < grid; b++) {
@@ -202,6 +205,8 @@ using std::max;
 inline void __syncthreads() { emu::blockBarrier(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warpBarrier(); }
 inline void __threadfence() {}
+inline void __threadfence_system() { __sync_synchronize(); }
+inline long long clock64() { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shflIdx(v, (unsigned)src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shflIdx(v, (emu::S().cur->tid % 32) ^ (unsigned)m); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) {
@@ -268,6 +273,12 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) {
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->t - a->t) * 1e3); return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1 };
+// "IPC" inside one process: the handle carries the pointer itself
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->multiProcessorCount = 1; strcpy(p->name, "cpu-emu"); return cudaSuccess; }
 

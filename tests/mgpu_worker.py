@@ -1,7 +1,8 @@
 """Worker for the multi-GPU parity test: launched with torchrun, one rank per GPU.
-  mgpu_worker.py N decomposed   every solve k-slab decomposed (diagonal-preconditioned CG, exchanges every iteration)
-  mgpu_worker.py N default      the shipping policy: multigrid viscosity solve replicated, pressure solve decomposed
-                                only above dist_min_unknowns per rank
+  mgpu_worker.py N default      the shipping path: multigrid-preconditioned viscosity solve and pressure solve cut into
+                                k-slabs, exchanges by peer-memory stores (xch.h)
+  mgpu_worker.py N diagonal     the same with the diagonal preconditioner (every iteration is stencil + exchanges)
+  FLIP_P2P=0                    no peer mapping: plain replicas
 Rank 0 also steps a single-GPU simulation and compares."""
 import os
 import sys
@@ -25,8 +26,7 @@ def main():
     phi, p = _analytic_scene(n)
     sim = FlipSim(n, n, n, 1.0 / n)
     sim.set_solid_sdf(phi); sim.set_particles(p); sim.set_viscosity(2.0)
-    if mode == "decomposed":
-        sim.set_param("dist_min_unknowns", 0)
+    if mode == "diagonal":
         sim.set_param("viscosity_precond", 0)
     box = [sim.dist_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
@@ -49,7 +49,7 @@ def main():
     if rank == 0:
         single = FlipSim(n, n, n, 1.0 / n)
         single.set_solid_sdf(phi); single.set_particles(p); single.set_viscosity(2.0)
-        if mode == "decomposed":
+        if mode == "diagonal":
             single.set_param("viscosity_precond", 0)
         for _ in range(3):
             single.advance(0.01)

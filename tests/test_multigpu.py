@@ -2,8 +2,9 @@
 
 CPU (gloo, world_size 2): the host-side plumbing bench.py uses — unique-id shipping with
 broadcast_object_list and the replica contract (two processes stepping the same scene produce
-bit-identical particles), on the CPU-emulation build.
-GPU (needs >= 2 devices): k-slab-decomposed solves against a single-GPU run, via torchrun.
+bit-identical particles), on the CPU-emulation build.  The sharded protocol itself is exercised on the CPU by
+tests/test_sharded_emu.py (ranks = threads of one process).
+GPU (needs >= 2 devices): the sharded substep against a single-GPU run, via torchrun.
 """
 import os
 import subprocess
@@ -55,20 +56,8 @@ def test_gloo_two_process_replicas(tmp_path):
     assert r.stdout.count("GLOO_OK") == 2
 
 
-def test_slab_bounds_cover_all_block_layers():
-    """same partition rule as dist_setup_slab (flipviscosity3d_b200/csrc/dist.cu)"""
-    for nbz in (1, 5, 9, 33, 65):
-        for nranks in (1, 2, 3, 4, 8):
-            if nranks > nbz:
-                continue
-            b = [(nbz * r // nranks, nbz * (r + 1) // nranks) for r in range(nranks)]
-            assert b[0][0] == 0 and b[-1][1] == nbz
-            assert all(b[i][1] == b[i + 1][0] for i in range(nranks - 1))
-            assert all(hi > lo for lo, hi in b)
-
-
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["decomposed", "default"])
+@pytest.mark.parametrize("mode", ["diagonal", "default"])
 def test_two_gpu_solves_match_single_gpu(mode):
     import torch
     if torch.cuda.device_count() < 2:
