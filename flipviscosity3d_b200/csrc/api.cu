@@ -64,6 +64,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s, s.vvalid, T);
     dev_alloc(s, s.vcoef, 4 * T);
     dev_alloc(s, s.vdiag, 3 * T);
+    dev_alloc(s, s.vmass, 3 * T);
     dev_alloc(s, s.ext_flag, (size_t)g.nblocks); dev_alloc(s, s.ext_flag2, (size_t)g.nblocks);
     dev_alloc(s, s.ext_list, (size_t)g.nblocks); dev_alloc(s, s.ext_count, 1);
     dev_alloc(s, s.blk_flag, (size_t)g.nblocks);
@@ -82,6 +83,8 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
     CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
+    CUDA_CHECK(cudaMallocHost((void **)&s.xch_status_host, sizeof(int)));
+    *s.xch_status_host = 0;
     *s.count_host = 0;
     *s.maxvel_host = 0;
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -123,6 +126,7 @@ void sim_free(Sim &s) {
     if (s.cgst_host) cudaFreeHost(s.cgst_host);
     if (s.count_host) cudaFreeHost(s.count_host);
     if (s.maxvel_host) cudaFreeHost(s.maxvel_host);
+    if (s.xch_status_host) cudaFreeHost(s.xch_status_host);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -540,6 +544,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "cg_variant_viscosity") { s.cg_variant_viscosity = (int)value; }
     else if (n == "cg_grid_mult") { s.cg_grid_mult = (int)value < 1 ? 1 : (int)value; s.xch_epoch++; }
     else if (n == "viscosity_precond") s.visc_precond = (int)value;
+    else if (n == "viscosity_operator") s.visc_operator = (int)value;
     else if (n == "viscosity_warm_start") s.visc_warm_start = (int)value;
     else if (n == "mg_sweeps") s.mg_sweeps = (int)value;
     else if (n == "mg_coarse_sweeps") s.mg_coarse_sweeps = (int)value;

@@ -655,8 +655,10 @@ static CGState run_cg(Sim &s, CGParams P, Diag diag, double tol_abs, double tol_
     int launched = 0;
     while (true) {
         CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        xch_status_fetch(s);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         h = *s.cgst_host;
+        if (xch_status_bad(s)) { h.fail = 1; h.converged = 0; break; }   // broken exchange: stop launching, xch_check reports it
         if (h.done || launched >= maxit + chunk) break;
 #ifndef FLIP_CPU_EMU
         if (use_graph) { CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream)); s.kernel_launches += s.cg_graph_launches[graph_slot]; }
@@ -840,8 +842,10 @@ static CGState run_cg2(Sim &s, CGParams P, Diag diag, double tol_abs, double tol
     int launched = 0;
     while (true) {
         CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        xch_status_fetch(s);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         h = *s.cgst_host;
+        if (xch_status_bad(s)) { h.fail = 1; h.converged = 0; break; }   // broken exchange: stop launching, xch_check reports it
         if (h.done || launched >= maxit + 2 * chunk) break;
 #ifndef FLIP_CPU_EMU
         if (use_graph) { CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)s.cg_graph[graph_slot], s.stream)); s.kernel_launches += s.cg_graph_launches[graph_slot]; }

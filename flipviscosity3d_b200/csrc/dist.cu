@@ -176,6 +176,12 @@ void xch_barrier(Sim &s) {
     s.kernel_launches++;
 }
 
+void xch_status_fetch(Sim &s) {
+    if (!s.sharded) return;
+    CUDA_CHECK(cudaMemcpyAsync(s.xch_status_host, &s.link->status, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+}
+bool xch_status_bad(Sim &s) { return s.sharded && *s.xch_status_host != 0; }
+
 void xch_check(Sim &s) {
     if (!s.sharded) return;
     int status = 0;
@@ -193,7 +199,6 @@ void dist_init(Sim &s, int rank, int nranks, const void *) {
     dist_shutdown(s);
     s.rank = rank; s.nranks = nranks;
     s.heap.rank = rank; s.heap.nranks = nranks;
-    emu::force_sync() = nranks > 1;
 }
 void dist_shutdown(Sim &s) {
     dist_p2p_shutdown(s);

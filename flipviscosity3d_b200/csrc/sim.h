@@ -47,6 +47,7 @@ struct Sim {
     int visc_maxit = 700;               // src/viscositysolver.h:202
     int visc_maxit_scale = 40;
     int visc_warm_start = 0;            // start the viscosity CG from the current velocity instead of 0
+    int visc_operator = 0;              // 0 = exact mass term (default), 1 = the reference's fp32-rounded diagonal (strict parity)
     int visc_precond = 2;               // 2 = Galerkin multigrid (gmg.h, default), 0 = diagonal
     int mg_sweeps = 2;                  // damped-Jacobi sweeps before = after the coarse correction
     int mg_coarse_sweeps = 24;
@@ -115,6 +116,7 @@ struct Sim {
     unsigned char *vvalid = 0;// dilated liquid mask
     float *vcoef = 0;         // 4 coefficient grids [4*total]: center, edgeU, edgeV, edgeW
     float *vdiag = 0;         // [3*total] row diagonals (0 = not an unknown)
+    float *vmass = 0;         // [3*total] mass term of every row as the CG operator applies it (viscosity.cu k_visc_rows)
     int *ext_flag = 0, *ext_flag2 = 0, *ext_list = 0, *ext_count = 0;   // extrapolation block list [nblocks] x3, [1]
     int *blk_flag = 0;        // [nblocks]
     int *blk_list = 0;        // [nblocks]
@@ -141,6 +143,7 @@ struct Sim {
     double **part_peers = 0;  // device table [FLIP_MAX_RANKS]: `part` of every rank
     unsigned long long xch_epoch = 1;   // bumped whenever the exchange set-up changes: captured graphs are keyed by it
     double xch_timeout_s = 20.0;        // a rank that waits longer than this for its peers gives up (Link::status)
+    int *xch_status_host = 0;           // pinned copy of Link::status, fetched with every convergence poll
 
     void *user_ev[4] = {0, 0, 0, 0};   // cudaEvent_t slots of flip_event_record (device-side timing for callers)
 
@@ -206,6 +209,8 @@ void xch_push_gather(Sim &s, const Grid &g, void *field, size_t elem, int ncomp,
 void xch_push_rows(Sim &s, const int *rng_dev, void *base, size_t row_bytes);                          // row range -> every rank
 void xch_barrier(Sim &s);                    // everything pushed so far has arrived everywhere
 void xch_check(Sim &s);                      // throws if a hand-shake timed out
+void xch_status_fetch(Sim &s);               // enqueue a copy of the hand-shake status next to a convergence poll ...
+bool xch_status_bad(Sim &s);                 // ... and read it after the stream synchronisation
 
 // substep driver (api.cu)
 void sim_substep(Sim &s, float dt);

@@ -159,9 +159,12 @@ __global__ void __launch_bounds__(256) k_visc_coefs(Grid g, const float *__restr
 }
 
 // rows: unknown test, diagonal, rhs (rhs goes to r)
+// vmass = the mass term the CG operator uses for every row (see k_visc_apply): the face volume itself (exact == 1, the
+// default), or what is left of it in the reference's fp32 diagonal, d_fp32 - (sum of the six factors) (exact == 0).
 __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restrict__ vvol, const float *__restrict__ vcoef,
                                                    const unsigned char *__restrict__ fstate, const float *__restrict__ vel,
-                                                   float *__restrict__ vdiag, double *__restrict__ rhs) {
+                                                   float *__restrict__ vdiag, double *__restrict__ rhs, float *__restrict__ vmass,
+                                                   int exact) {
     int i, j, k;
     if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
     int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
@@ -172,12 +175,14 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
     const float *u = vel, *v = vel + T, *w = vel + 2 * T;
     bool interior = i >= 1 && i < g.ni && j >= 1 && j < g.nj && k >= 1 && k < g.nk;
     float dU = 0, dV = 0, dW = 0;
+    float mU = 0, mV = 0, mW = 0;
     double bU = 0, bV = 0, bW = 0;
     if (interior && su[id] == 0) {
         float vol = vvol[VU * T + id];
         if (vol > 0 || vc[id] > 0 || vc[id - 1] > 0 || vew[id + sy] > 0 || vew[id] > 0 || vev[id + sz] > 0 || vev[id] > 0) {
             float fR = cc[id], fL = cc[id - 1], fT = cw[id + sy], fB = cw[id], fF = cv[id + sz], fK = cv[id];
             dU = vol + fR + fL + fT + fB + fF + fK;
+            mU = exact ? vol : (float)((double)dU - ((double)fR + (double)fL + (double)fT + (double)fB + (double)fF + (double)fK));
             float r = vol * u[id];
             if (su[id + 1]) r -= -fR * u[id + 1];
             if (su[id - 1]) r -= -fL * u[id - 1];
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
         if (vol > 0 || vew[id + 1] > 0 || vew[id] > 0 || vc[id] > 0 || vc[id - sy] > 0 || veu[id + sz] > 0 || veu[id] > 0) {
             float fR = cw[id + 1], fL = cw[id], fT = cc[id], fB = cc[id - sy], fF = cu[id + sz], fK = cu[id];
             dV = vol + fR + fL + fT + fB + fF + fK;
+            mV = exact ? vol : (float)((double)dV - ((double)fR + (double)fL + (double)fT + (double)fB + (double)fF + (double)fK));
             float r = vol * v[id];
             if (sv[id + 1]) r -= -fR * v[id + 1];
             if (sv[id - 1]) r -= -fL * v[id - 1];
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
         if (vol > 0 || vev[id + 1] > 0 || vev[id] > 0 || veu[id + sy] > 0 || veu[id] > 0 || vc[id] > 0 || vc[id - sz] > 0) {
             float fR = cv[id + 1], fL = cv[id], fT = cu[id + sy], fB = cu[id], fF = cc[id], fK = cc[id - sz];
             dW = vol + fR + fL + fT + fB + fF + fK;
+            mW = exact ? vol : (float)((double)dW - ((double)fR + (double)fL + (double)fT + (double)fB + (double)fF + (double)fK));
             float r = vol * w[id];
             if (sw[id + 1]) r -= -fR * w[id + 1];
             if (sw[id - 1]) r -= -fL * w[id - 1];
@@ -243,6 +250,7 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
         }
     }
     vdiag[id] = dU; vdiag[T + id] = dV; vdiag[2 * T + id] = dW;
+    vmass[id] = mU; vmass[T + id] = mV; vmass[2 * T + id] = mW;
     rhs[id] = dU != 0.0f ? bU : 0.0;
     rhs[T + id] = dV != 0.0f ? bV : 0.0;
     rhs[2 * T + id] = dW != 0.0f ? bW : 0.0;
@@ -250,16 +258,21 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
 
 // phase A: q = A s for the three face families of each cell index
 //
-// Every row is evaluated in DIFFERENCE form,  q = vol * s0 + sum_k f_k (s0 - s_k) + cross differences,  which is
+// Every row is evaluated in DIFFERENCE form,  q = mass * s0 + sum_k f_k (s0 - s_k) + cross differences,  which is
 // the same row as  d * s0 - sum_k f_k s_k - ...  with d = vol + sum_k f_k  (src/viscositysolver.cpp:429) in exact
 // arithmetic.  The reference forms d in fp32; at 256^3 the six factors add up to ~2e4, ulp(2e4) = 2e-3, so the
-// face-volume ("mass") term vol <= 1 of every row is rounded to within +-1e-3 and comes out NEGATIVE on thousands
-// of thin free-surface faces: the assembled matrix is no longer positive definite, CG wanders (measured on a scipy
-// copy of the system: 64 multigrid-PCG iterations with the exact diagonal, 307 with the fp32 one, Jacobi-PCG 3484
-// vs 5686) and the reference's own MICCG(0) stops at its 700-iteration cap.  The difference form keeps the mass
-// term exact; the two operators differ by that rounding noise only (<= 1e-7 relative per diagonal entry).
+// face-volume ("mass") term vol <= 1 of every row is rounded to within +-1e-3 and comes out NEGATIVE on thousands of thin
+// free-surface faces: the assembled matrix loses its diagonal dominance there and CG needs several times more iterations
+// (measured on a scipy copy of the system: 64 multigrid-PCG iterations with the exact diagonal, 307 with the fp32 one,
+// Jacobi-PCG 3484 vs 5686; the reference's own MICCG(0) needs 8693 at 256^3, far beyond its 700-iteration cap).  The
+// difference form takes the mass term as a separate field, `vmass` (k_visc_rows):
+//   viscosity_operator = 0 (default)  vmass = vol, the exact row;
+//   viscosity_operator = 1            vmass = d_fp32 - sum of the factors: bit for bit the reference's rounded row, for
+//                                     strict parity runs (tests/test_parity_regime.py).
+// The two differ by the reference's rounding noise only (<= 1e-7 relative per diagonal entry), which in the stiff regime
+// moves the SOLUTION by ~3e-5 (measured: profiles/r2_parity_*.json).
 __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const float *__restrict__ vcoef,
-                                                           const float *__restrict__ vdiag, const float *__restrict__ vvol, int parity) {
+                                                           const float *__restrict__ vdiag, const float *__restrict__ vmass, int parity) {
     __shared__ double sm[CG_THREADS / 32];
     if (P.st[parity].done) return;
     if (!xch_enter(P.X)) return;
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
         const double ew0 = cw[id], ew_xp = cw[id + 1], ew_yp = cw[id + sy];
         if (dU != 0.0f) {
             const double fR = c0, fL = c_xm, fT = ew_yp, fB = ew0, fF = ev_zp, fK = ev0;
-            double q = (double)vvol[T + id] * u0 + fR * (u0 - u_xp) + fL * (u0 - u_xm) + fT * (u0 - u_yp) + fB * (u0 - u_ym) +
+            double q = (double)vmass[id] * u0 + fR * (u0 - u_xp) + fL * (u0 - u_xm) + fT * (u0 - u_yp) + fB * (u0 - u_ym) +
                        fF * (u0 - u_zp) + fK * (u0 - u_zm) - fT * (v_yp - v_xm_yp) + fB * (v0 - v_xm) - fF * (w_zp - w_xm_zp) +
                        fK * (w0 - w_xm);
             P.q[id] = q;
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
         }
         if (dV != 0.0f) {
             const double fR = ew_xp, fL = ew0, fT = c0, fB = c_ym, fF = eu_zp, fK = eu0;
-            double q = (double)vvol[2 * T + id] * v0 + fR * (v0 - v_xp) + fL * (v0 - v_xm) + fT * (v0 - v_yp) + fB * (v0 - v_ym) +
+            double q = (double)vmass[T + id] * v0 + fR * (v0 - v_xp) + fL * (v0 - v_xm) + fT * (v0 - v_yp) + fB * (v0 - v_ym) +
                        fF * (v0 - v_zp) + fK * (v0 - v_zm) - fR * (u_xp - u_xp_ym) + fL * (u0 - u_ym) - fF * (w_zp - w_ym_zp) +
                        fK * (w0 - w_ym);
             P.q[T + id] = q;
@@ -307,7 +320,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
         }
         if (dW != 0.0f) {
             const double fR = ev_xp, fL = ev0, fT = eu_yp, fB = eu0, fF = c0, fK = c_zm;
-            double q = (double)vvol[3 * T + id] * w0 + fR * (w0 - w_xp) + fL * (w0 - w_xm) + fT * (w0 - w_yp) + fB * (w0 - w_ym) +
+            double q = (double)vmass[2 * T + id] * w0 + fR * (w0 - w_xp) + fL * (w0 - w_xm) + fT * (w0 - w_yp) + fB * (w0 - w_ym) +
                        fF * (w0 - w_zp) + fK * (w0 - w_zm) - fR * (u_xp - u_xp_zm) + fL * (u0 - u_zm) - fT * (v_yp - v_yp_zm) +
                        fB * (v0 - v_zm);
             P.q[2 * T + id] = q;
@@ -682,8 +695,10 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
     int launched = 0;
     while (true) {
         CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+        xch_status_fetch(s);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         h = *s.cgst_host;
+        if (xch_status_bad(s)) { h.fail = 1; h.converged = 0; break; }   // broken exchange: stop launching, xch_check reports it
         if (s.verbose > 1) printf("\t\tmg-pcg iteration %d max|r| %.3e (tol %.3e)\n", h.iter, h.resid, h.tol), fflush(stdout);
         if (h.done || launched >= maxit + chunk) break;
 #ifndef FLIP_CPU_EMU
@@ -725,23 +740,23 @@ void stage_apply_viscosity(Sim &s, float dt) {
     long long n1 = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
     FLIP_LAUNCH(k_visc_coefs, cdiv(n1, 256), 256, s.stream, g, (const float *)s.viscosity, (const float *)s.vvol, s.vcoef, factor);
     FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, g, (const float *)s.vvol, (const float *)s.vcoef,
-                (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r);
+                (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0);
     s.kernel_launches += 2;
     DiagViscosity diag{s.vdiag, g.total};
     build_block_list<3>(s, diag);
     CUDA_CHECK(cudaMemsetAsync(s.cg_s, 0, sizeof(double) * 3 * (size_t)g.total, s.stream));
     CGParams P = cg_params(s, 0);
     int G = cg_grid(s);
-    const float *vcoef = s.vcoef, *vdiag = s.vdiag, *vvol = s.vvol;
+    const float *vcoef = s.vcoef, *vdiag = s.vdiag, *vmass = s.vmass;
     cudaStream_t st = s.stream;
     int maxit = s.visc_maxit * s.visc_maxit_scale;
     CGState h;
     // phase A of an iteration: ghost planes of the search direction (U, V and W: rows couple components at k +- 1),
     // then the stencil
     auto apply_on = [&](CGParams &Q) {
-        return [&s, &Q, G, st, vcoef, vdiag, vvol](int parity) {
+        return [&s, &Q, G, st, vcoef, vdiag, vmass](int parity) {
             xch_push_halo(s, s.g, Q.s, sizeof(double), 3, 0, 1);
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Q, vcoef, vdiag, vvol, parity);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, st, Q, vcoef, vdiag, vmass, parity);
             s.kernel_launches++;
         };
     };
@@ -800,7 +815,7 @@ extern "C" int flip_debug_visc_apply(void *hsim, const double *x_host, double *y
         CGParams P = cg_params(s, 0);
         P.s = s.cg_z; P.q = s.cg_w;
         P.X.nranks = 1;   // debug helper: whole field on this rank, no hand-shakes
-        FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
+        FLIP_LAUNCH_SYNC(k_visc_apply, cg_grid(s), CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vmass, 0);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(y_host, s.cg_w, n * sizeof(double), cudaMemcpyDeviceToHost));
     } catch (...) { return -2; }
@@ -813,7 +828,7 @@ extern "C" int flip_debug_visc_rhs(void *hsim, double *b_host, float *diag_host,
     try {
         long long n1 = (long long)(s.g.ni + 1) * (s.g.nj + 1) * (s.g.nk + 1);
         FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, s.g, (const float *)s.vvol, (const float *)s.vcoef,
-                    (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r);
+                    (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(b_host, s.cg_r, 3 * T * sizeof(double), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(diag_host, s.vdiag, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
@@ -870,10 +885,10 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         P.X.nranks = 1;   // timing helper: this rank's cells, no hand-shakes
         CUDA_CHECK(cudaMemsetAsync(s.cgst, 0, 2 * sizeof(CGState), s.stream));
         int G = cg_grid(s);
-        FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
+        FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vmass, 0);
         CUDA_CHECK(cudaEventRecord(e0, s.stream));
         for (int k = 0; k < reps; k++)
-            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vvol, 0);
+            FLIP_LAUNCH_SYNC(k_visc_apply, G, CG_THREADS, s.stream, P, (const float *)s.vcoef, (const float *)s.vdiag, (const float *)s.vmass, 0);
         CUDA_CHECK(cudaEventRecord(e1, s.stream));
         *alg_bytes = (unsigned long long)s.visc_stats.unknowns * (2 * 8 + 16);
     } else {

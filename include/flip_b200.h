@@ -133,6 +133,8 @@ int flip_set_valid(flip_sim *h, int comp, const uint8_t *in);
  * names: "pressure_tol" "pressure_maxit" "viscosity_tol" "viscosity_maxit" "viscosity_accept"
  *        "maxit_scale" "cg_chunk" "pic_ratio" "cfl" "verbose"   (defaults = the reference's)
  *        "viscosity_precond" 2 = Galerkin multigrid (default), 0 = diagonal;
+ *        "viscosity_operator" 0 = rows with the exact face-volume term (default), 1 = rows with the reference's
+ *        fp32-rounded diagonal, bit for bit (strict parity in the stiff regime, several times more iterations);
  *        "mg_sweeps" "mg_coarse_sweeps" "mg_omega" "mg_levels" "mg_chunk" "mg_flexible" tune the V-cycle */
 int flip_set_param(flip_sim *h, const char *name, double value);
 int flip_get_stats(flip_sim *h, flip_stats *out);

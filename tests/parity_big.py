@@ -55,15 +55,17 @@ def run(path, lib=None):
     refs = {t: get(t) for t in ("ref700", "ref1e6", "ref1e8")}
     res["oracle_truncated_vs_oracle_converged"] = diff(refs["ref700"], refs["ref1e8"])
     res["oracle_1e6_vs_oracle_1e8"] = diff(refs["ref1e6"], refs["ref1e8"])
-    for tol in (1e-6, 1e-8):
+    # operator 0 = rows with the exact mass term (the default), 1 = the reference's fp32-rounded diagonal (strict parity)
+    for op, tol in ((0, 1e-6), (0, 1e-8), (1, 1e-8)):
         sim.set_field(F.F_LIQUID_SDF, phi)
         sim.set_mac(*pre)
         sim.set_param("viscosity_tol", tol)
+        sim.set_param("viscosity_operator", op)
         t0 = time.perf_counter()
         sim.apply_viscosity(dt)
         st = sim.stats()
         got = sim.get_mac()
-        key = "library_tol%g" % tol
+        key = ("library_tol%g" % tol) if op == 0 else ("library_reference_operator_tol%g" % tol)
         res[key] = {"iterations": st["viscosity_iterations"], "converged": st["viscosity_converged"], "applied": st["viscosity_applied"],
                     "residual": st["viscosity_residual"], "rhs_max": st["viscosity_rhs_max"], "unknowns": st["viscosity_unknowns"],
                     "solve_ms": st["viscosity_solve_ms"], "wall_s": time.perf_counter() - t0,
@@ -71,6 +73,7 @@ def run(path, lib=None):
                     "linf_vs_oracle_1e8": diff(got, refs["ref1e8"]), "linf_vs_oracle_1e6": diff(got, refs["ref1e6"]),
                     "linf_vs_oracle_truncated_700": diff(got, refs["ref700"])}
     sim.set_param("viscosity_tol", 1e-6)
+    sim.set_param("viscosity_operator", 0)
     # pressure stage from the oracle's tightest viscosity result
     sim.set_field(F.F_LIQUID_SDF, phi)
     sim.set_mac(*refs["ref1e8"])

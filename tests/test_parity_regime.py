@@ -3,8 +3,15 @@ the oracle's raised-cap solves ("truncated reference solves
 the same stiffness as 256^3 / viscosity 5 and is what the regular -m gpu suite runs; the 256^3 fixture itself is checked
 when present (tests/golden_big/ is generated on the CPU by tests/golden/make_parity_big.py and is git-ignored).
 
-Tolerances: velocities are O(1) m/s (max |u| ~ 0.2-0.3 here).  Library (multigrid-PCG, tol 1e-8 relative residual) vs oracle
-(MICCG(0), tol 1e-8, cap raised): 5e-6 absolute on the faces bordering fluid.  Pressure: 1e-6 relative to max|p|."""
+Tolerances (velocities: max |u| ~ 0.2 here), on the faces bordering fluid:
+  * library with the reference's own rows (viscosity_operator = 1: the fp32-rounded diagonal of
+    src/viscositysolver.cpp:429, bit for bit), multigrid-PCG at tol 1e-8, vs oracle (MICCG(0), tol 1e-8, cap raised):
+    5e-6 absolute;
+  * library with its default rows (exact face-volume term): 1e-4 absolute.  In this regime the six factors of a row add
+    up to ~2e4, so the reference's fp32 diagonal carries +-1e-3 of rounding noise against a mass term <= 1; that noise
+    alone moves the reference's SOLUTION by ~3e-5 (measured: library default vs library with the reference's rows).
+    The default keeps the better-conditioned exact rows; the strict mode exists to prove the two coincide otherwise;
+  * pressure: 1e-6 relative to max|p|."""
 import glob
 import os
 
@@ -16,13 +23,13 @@ BIG = os.path.join(common.ROOT, "tests", "golden_big")
 
 
 def _check(res):
-    lib8 = res["library_tol1e-08"]
-    assert lib8["converged"] == 1 and lib8["applied"] == 1 and lib8["same_unknown_set_as_oracle"]
-    assert lib8["linf_vs_oracle_1e8"] <= 5e-6, res
-    lib6 = res["library_tol1e-06"]
-    assert lib6["converged"] == 1
-    # at the shipping tolerance the library is at least as close to the converged answer as the reference's own 1e-6 solve
-    assert lib6["linf_vs_oracle_1e8"] <= max(2 * res["oracle_1e6_vs_oracle_1e8"], 2e-5), res
+    strict = res["library_reference_operator_tol1e-08"]
+    assert strict["converged"] == 1 and strict["applied"] == 1 and strict["same_unknown_set_as_oracle"]
+    assert strict["linf_vs_oracle_1e8"] <= 5e-6, res
+    for key in ("library_tol1e-08", "library_tol1e-06"):
+        lib = res[key]
+        assert lib["converged"] == 1 and lib["applied"] == 1 and lib["same_unknown_set_as_oracle"]
+        assert lib["linf_vs_oracle_1e8"] <= 1e-4, res
     assert res["pressure"]["converged"] == 1 and res["pressure"]["linf_relative"] <= 1e-6, res
 
 
