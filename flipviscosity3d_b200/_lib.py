@@ -38,6 +38,12 @@ SYMBOLS = {
     "flip_set_solid_sdf": (C.c_int, [_H, _FP]),
     "flip_set_particles": (C.c_int, [_H, _FP, C.c_int64]),
     "flip_get_particles": (C.c_int, [_H, _FP, C.c_int64, C.POINTER(C.c_int64)]),
+    "flip_reset_boundary": (C.c_int, [_H]),
+    "flip_add_boundary_mesh": (C.c_int, [_H, _FP, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int]),
+    "flip_add_liquid_mesh": (C.c_int, [_H, _FP, C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int64)]),
+    "flip_mesh_sdf": (C.c_int, [_H, _FP, C.c_int, C.POINTER(C.c_int32), C.c_int, _FP]),
+    "flip_srand": (C.c_int, [C.c_uint]),
+    "flip_rand": (C.c_int, []),
     "flip_num_particles": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "flip_set_viscosity_uniform": (C.c_int, [_H, C.c_float]),
     "flip_set_viscosity_grid": (C.c_int, [_H, _FP]),

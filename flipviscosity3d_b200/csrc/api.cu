@@ -392,6 +392,37 @@ int flip_get_particles(flip_sim *h, float *aos, int64_t capacity, int64_t *n_out
     API_END()
 }
 
+int flip_reset_boundary(flip_sim *h) {
+    API_BEGIN(h)
+    scene_reset_boundary(s);
+    API_END()
+}
+
+int flip_add_boundary_mesh(flip_sim *h, const float *verts, int nv, const int *tris, int nt, int inverted) {
+    API_BEGIN(h)
+    if (!verts || !tris) return fail_inval(s, "flip_add_boundary_mesh: null pointer");
+    scene_add_boundary(s, verts, nv, tris, nt, inverted != 0);
+    API_END()
+}
+
+int flip_add_liquid_mesh(flip_sim *h, const float *verts, int nv, const int *tris, int nt, int64_t *added_out) {
+    API_BEGIN(h)
+    if (!verts || !tris) return fail_inval(s, "flip_add_liquid_mesh: null pointer");
+    long long n = scene_add_liquid(s, verts, nv, tris, nt);
+    if (added_out) *added_out = n;
+    API_END()
+}
+
+int flip_mesh_sdf(flip_sim *h, const float *verts, int nv, const int *tris, int nt, float *out_nodal) {
+    API_BEGIN(h)
+    if (!verts || !tris || !out_nodal || nv <= 0 || nt <= 0) return fail_inval(s, "flip_mesh_sdf: bad arguments");
+    scene_mesh_sdf(s, verts, nv, tris, nt, out_nodal);
+    API_END()
+}
+
+int flip_srand(unsigned int seed) { scene_srand(seed); return FLIP_OK; }
+int flip_rand(void) { return scene_rand_next(); }
+
 int flip_num_particles(flip_sim *h, int64_t *n_out) {
     if (!h || !n_out) return FLIP_EINVAL;
     *n_out = h->s.np;
@@ -556,6 +587,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_flexible") s.mg_flexible = (int)value;
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
     else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // unmap the peers: plain replicas again
+    else if (n == "shard_min_unknowns") s.shard_min_unknowns = (long long)value;
     else if (n == "xch_timeout_s") s.xch_timeout_s = value;                    // takes effect at the next flip_dist_p2p_import
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;

@@ -586,7 +586,7 @@ static CGParams cg_params(Sim &s, int strict) {
 
 // A CUDA graph of an iteration chunk is only valid for the exchange set-up it was captured under
 static inline unsigned long long cg_graph_tag(Sim &s, int chunk, int variant) {
-    return (unsigned long long)chunk * 4 + variant + ((unsigned long long)s.xch_epoch << 20);
+    return (unsigned long long)chunk * 8 + variant * 2 + (s.sharded ? 1 : 0) + ((unsigned long long)s.xch_epoch << 20);
 }
 
 // Generic driver.  `apply(parity)` launches the phase-A kernel (q = A s and the s.q partials); on several ranks it also

@@ -107,6 +107,8 @@ __global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const 
 
 void solve_pressure(Sim &s, float dt) {
     const Grid &g = s.g;
+    // small systems are not worth their hand-shakes: every rank solves the whole system (sim.h shard_min_unknowns)
+    ReplicateGuard replicate(s, s.sharded && (long long)s.pres_last_unknowns < s.shard_min_unknowns);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
@@ -162,6 +164,7 @@ void solve_pressure(Sim &s, float dt) {
     s.pres_stats.iters = h.iter; s.pres_stats.converged = h.converged; s.pres_stats.resid = h.resid;
     s.pres_stats.bmax = h.bmax; s.pres_stats.skipped = (h.iter == 0 && h.converged) ? 1 : 0;
     s.pres_stats.blocks = s.count_host[0]; s.pres_stats.unknowns = s.count_host[1];
+    s.pres_last_unknowns = s.count_host[1];
     s.pres_stats.ms = ms;
     if (s.verbose) {
         printf("\tpressure: %d iterations, max|r| %.3e, %s (%d active blocks, %.3f ms)\n", h.iter, h.resid,

@@ -9,6 +9,7 @@
 //               rank has (their counters are stored into this rank's Link by their last CTAs), i.e. until everything this
 //               kernel may read was delivered and nobody still reads what this kernel may overwrite remotely;
 //   xch_leave   the last CTA to finish bumps this rank's counter and stores it into every peer's Link.
+// Pushes (k_push_planes / k_push_rows) only leave: see the note above k_push_planes.
 //
 // One NVLink store per peer and kernel; no host involvement, no NCCL on the substep path, no separate all-reduce kernels:
 // reduction partials are pushed by the producing kernel (cg.h part_store) and re-reduced in a fixed rank-major order by
@@ -68,12 +69,14 @@ FLIP_D bool xch_enter(const Xch &X) {
     return xch_ok_s != 0;
 }
 
-// all threads of the CTA, at the very end.  remote_stores: this kernel stored into peer memory.
+// all threads of the CTA, at the very end.  remote_stores: this kernel stored into peer memory.  The block barrier orders
+// every thread's stores before thread 0's system-scope fence (fences are cumulative), so one fence per CTA publishes them
+// all - a fence in every thread costs microseconds per kernel.
 FLIP_D void xch_leave(const Xch &X, bool remote_stores) {
     if (X.nranks == 1) return;
-    if (remote_stores) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (remote_stores) __threadfence_system();
         unsigned int prev = atomicAdd(&X.local->cta_done, 1u);
         if (prev == gridDim.x - 1) {
             X.local->cta_done = 0;
@@ -149,8 +152,11 @@ struct PushDesc {
     int pz;                          // ghost planes below plane 0 in the padded layout (FLIP_PZ)
 };
 
+// A push does not wait (no xch_enter): it follows, in stream order, the kernel that produced the planes, and no kernel
+// reads the ghost planes of the field it produces, so by the time the producer could start (its own xch_enter) every
+// rank had finished the last reader of the old ghost values.  The consumers' xch_enter waits for the pushes to land.
 static __global__ void __launch_bounds__(256) k_push_planes(Xch X, const Cuts *__restrict__ cuts, PushDesc d) {
-    if (!xch_enter(X)) return;
+    if (((volatile Link *)X.local)->status) return;
     const int c0 = cuts->c[d.level][X.rank], c1 = cuts->c[d.level][X.rank + 1];
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     for (int t = 0; t < X.nranks; t++) {
@@ -175,7 +181,7 @@ static __global__ void __launch_bounds__(256) k_push_planes(Xch X, const Cuts *_
 // Pushes a contiguous range of ROWS (explicit multigrid levels: coefficient rows, smoothing weights) of this rank to every
 // other rank.  The range is read from device memory: rng[0] .. rng[1] in units of `row_bytes` (a multiple of 16).
 static __global__ void __launch_bounds__(256) k_push_rows(Xch X, const int *__restrict__ rng, const char *src, PushDesc d, size_t row_bytes) {
-    if (!xch_enter(X)) return;
+    if (((volatile Link *)X.local)->status) return;
     const size_t off = (size_t)rng[0] * row_bytes, n16 = (size_t)(rng[1] - rng[0]) * row_bytes / 16;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     const int4 *__restrict__ s = (const int4 *)(src + off);

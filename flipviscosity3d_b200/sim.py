@@ -90,6 +90,36 @@ class FlipSim:
         self._ck(self.lib.flip_get_particles(self.h, _fp(out), len(out), C.byref(m)))
         return out[: m.value]
 
+    # ---- scene construction on the device (csrc/scene.cu) ----
+    @staticmethod
+    def _mesh(verts, tris):
+        verts = np.ascontiguousarray(verts, np.float32); tris = np.ascontiguousarray(tris, np.int32)
+        assert verts.ndim == 2 and verts.shape[1] == 3 and tris.ndim == 2 and tris.shape[1] == 3
+        return verts, tris, _fp(verts), tris.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def reset_boundary(self):
+        """the domain-box boundary FluidSimulation::initialize / resetBoundary builds"""
+        self._ck(self.lib.flip_reset_boundary(self.h))
+
+    def add_boundary(self, verts, tris, inverted=False):
+        verts, tris, vp, tp = self._mesh(verts, tris)
+        self._ck(self.lib.flip_add_boundary_mesh(self.h, vp, len(verts), tp, len(tris), int(inverted)))
+
+    def add_liquid(self, verts, tris):
+        verts, tris, vp, tp = self._mesh(verts, tris)
+        n = C.c_int64()
+        self._ck(self.lib.flip_add_liquid_mesh(self.h, vp, len(verts), tp, len(tris), C.byref(n)))
+        return n.value
+
+    def mesh_sdf(self, verts, tris):
+        verts, tris, vp, tp = self._mesh(verts, tris)
+        out = np.empty(self.field_shape(F_SOLID_SDF), np.float32)
+        self._ck(self.lib.flip_mesh_sdf(self.h, vp, len(verts), tp, len(tris), _fp(out)))
+        return out
+
+    def srand(self, seed=1):
+        self.lib.flip_srand(C.c_uint(seed))
+
     def set_viscosity(self, v):
         if np.isscalar(v):
             self._ck(self.lib.flip_set_viscosity_uniform(self.h, C.c_float(v)))

@@ -101,6 +101,23 @@ int flip_set_viscosity_grid(flip_sim *h, const float *v_nodesized);
 /* setGravity (src/fluidsimulation.cpp:126-132) */
 int flip_set_gravity(flip_sim *h, float gx, float gy, float gz);
 
+/* ---- scene construction on the device (optional: flip_set_solid_sdf / flip_set_particles take host-built scenes) ----
+ * Same results as the reference's init-time code wherever the substep can tell the difference (csrc/scene.cu): exact
+ * point-triangle distances and crossing-parity signs (MeshLevelSet::calculateSignedDistanceField,
+ * src/meshlevelset.cpp:138-347), the reference's seeding order and libc rand() sequence.  Meshes: nv x 3 float vertices,
+ * nt x 3 int32 vertex indices, inside the domain (else FLIP_EINVAL, where the reference asserts).
+ * flip_reset_boundary = FluidSimulation::resetBoundary / the boundary initialize() builds (src/fluidsimulation.cpp:60-62,
+ * 198-239); flip_add_boundary_mesh = addBoundary (:45-58); flip_add_liquid_mesh = addLiquid (:64-97), appending to the
+ * particles already loaded (before the first substep). */
+int flip_reset_boundary(flip_sim *h);
+int flip_add_boundary_mesh(flip_sim *h, const float *verts, int nv, const int32_t *tris, int nt, int inverted);
+int flip_add_liquid_mesh(flip_sim *h, const float *verts, int nv, const int32_t *tris, int nt, int64_t *added_out);
+/* nodal signed distance of a mesh on the handle's grid, (ni+1)(nj+1)(nk+1) floats, x fastest (tests, tools) */
+int flip_mesh_sdf(flip_sim *h, const float *verts, int nv, const int32_t *tris, int nt, float *out_nodal);
+/* the library's restatement of glibc rand() that seeding draws from: process-wide like libc's, unseeded = srand(1) */
+int flip_srand(unsigned int seed);
+int flip_rand(void);
+
 /* ---- time stepping ---- */
 /* FluidSimulation::advance(float dt) (src/fluidsimulation.cpp:135-168): CFL substep loop */
 int flip_advance(flip_sim *h, float dt, int *substeps_out);

@@ -68,6 +68,8 @@ def test_sharded_frames_match_single_rank(emu_lib, nranks):
     setup = _scene_setup(n, 2.0)
 
     def work(sim):
+        if nranks == 3:
+            sim.set_param("shard_min_unknowns", 0)  # 3 ranks: pressure solve sharded as well; 2 ranks: the default policy
         for _ in range(2):
             sim.advance(0.01)
         st = sim.stats()
@@ -95,6 +97,7 @@ def test_sharded_viscosity_solve_tight(emu_lib, precond):
     def work(sim):
         sim.set_param("viscosity_precond", precond)
         sim.set_param("viscosity_tol", 1e-10)
+        sim.set_param("shard_min_unknowns", 0)      # cut the (small) pressure system into slabs too
         sim.update_liquid_sdf(); sim.advect_velocity_field(); sim.add_body_force(0.01)
         sim.apply_viscosity(0.01)
         a = [x.copy() for x in sim.get_mac()]
