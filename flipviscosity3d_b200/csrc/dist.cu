@@ -305,3 +305,68 @@ void dist_shutdown(Sim &s) {
     s.heap.rank = 0; s.heap.nranks = 1;
 }
 #endif
+
+// ---- exchange micro-benchmark (dev tool, tests/gpu_dev_xch.py): what one synchronising kernel costs ----------------
+#ifndef FLIP_CPU_EMU
+static __global__ void __launch_bounds__(512) k_xb_plain(int dummy) {
+    if (dummy == 12345 && threadIdx.x == 0) printf("never\n");
+}
+static __global__ void __launch_bounds__(512) k_xb_enter_leave(Xch X, int fence) {
+    if (!xch_enter(X)) return;
+    xch_leave(X, fence != 0);
+}
+static __global__ void __launch_bounds__(512) k_xb_leave_only(Xch X, int fence) { xch_leave(X, fence != 0); }
+// every thread stores one float into the upper/lower neighbour's copy of `buf` (coalesced or strided), then leave
+static __global__ void __launch_bounds__(512) k_xb_scatter(Xch X, float *peer_buf, int stride) {
+    if (!xch_enter(X)) return;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    peer_buf[t * (size_t)stride] = (float)t;
+    xch_leave(X, true);
+}
+extern "C" int flip_debug_xch_bench(void *hsim, int mode, int reps, int ctas, float *us_per_kernel) {
+    Sim &s = *(Sim *)hsim;
+    try {
+        Xch X = xch_of(s);
+        float *buf = s.vnode;
+        float *peer = s.sharded ? s.heap.peer((s.rank + 1) % s.nranks, buf) : buf;
+        PushDesc d;
+        Grid g = s.g;
+        auto launch = [&]() {
+            switch (mode) {
+                case 0: k_xb_plain<<<ctas, 512, 0, s.stream>>>(0); break;
+                case 1: k_xb_enter_leave<<<ctas, 512, 0, s.stream>>>(X, 0); break;
+                case 2: k_xb_enter_leave<<<ctas, 512, 0, s.stream>>>(X, 1); break;
+                case 3: k_xb_leave_only<<<ctas, 512, 0, s.stream>>>(X, 0); break;
+                case 4: k_xb_leave_only<<<ctas, 512, 0, s.stream>>>(X, 1); break;
+                case 5: xch_push_halo(s, g, s.cg_s, sizeof(double), 3, 0, 1); break;      // fp64 search direction, 1 plane each way
+                case 6: k_xb_scatter<<<ctas, 512, 0, s.stream>>>(X, peer, 1); break;       // coalesced 4-byte remote stores
+                case 7: k_xb_scatter<<<ctas, 512, 0, s.stream>>>(X, peer, 8); break;       // one store per 32-byte sector
+                case 8: xch_barrier(s); break;
+                case 9: xch_push_halo(s, g, s.vnode, sizeof(float), 3, 0, 1); break;       // fp32 level-0 iterate, 1 plane each way
+            }
+        };
+        xch_update_cuts(s);
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        for (int r = 0; r < reps; r++) launch();
+        CUDA_CHECK(cudaStreamEndCapture(s.stream, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphLaunch(exec, s.stream));   // warm-up
+        CUDA_CHECK(cudaStreamSynchronize(s.stream));
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaEventRecord(e0, s.stream));
+        CUDA_CHECK(cudaGraphLaunch(exec, s.stream));
+        CUDA_CHECK(cudaEventRecord(e1, s.stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        *us_per_kernel = ms * 1e3f / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        xch_check(s);
+    } catch (const std::exception &e) { s.last_error = e.what(); return -2; }
+    return 0;
+}
+#endif

@@ -39,8 +39,23 @@ struct Xch {
 #ifdef FLIP_CPU_EMU
 #include <sched.h>
 #define XCH_SPIN_PAUSE() sched_yield()
+FLIP_D unsigned long long xch_ld_acquire(const volatile unsigned long long *p) { unsigned long long v = *p; __sync_synchronize(); return v; }
+FLIP_D void xch_st_relaxed(volatile unsigned long long *p, unsigned long long v) { *p = v; }
+FLIP_D void xch_fence() { __sync_synchronize(); }
 #else
 #define XCH_SPIN_PAUSE()
+// System-scope primitives in PTX: __threadfence_system() is MEMBAR.SC.SYS + an L1 invalidate in every thread that calls
+// it; the hand-shake only needs an acquire load of the flag (LDG.STRONG.SYS + CCTL.IVALL, no barrier) and ONE release
+// fence (MEMBAR.ALL.SYS) per CTA that stored into peer memory.
+FLIP_D unsigned long long xch_ld_acquire(const volatile unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+FLIP_D void xch_st_relaxed(volatile unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+FLIP_D void xch_fence() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 #endif
 
 // all threads of the CTA; false = the exchange is broken (time-out somewhere): return without doing anything
@@ -56,12 +71,11 @@ FLIP_D bool xch_enter(const Xch &X) {
             const long long t0 = clock64(), lim = L->timeout_cycles;
             for (int src = 0; src < X.nranks && ok; src++) {
                 if (src == X.rank) continue;
-                while (L->arrive[src] < want) {
+                while (xch_ld_acquire(&L->arrive[src]) < want) {   // acquire: what the peer stored before its flag is visible
                     if (clock64() - t0 > lim) { L->status = 1; ok = 0; break; }
                     XCH_SPIN_PAUSE();
                 }
             }
-            __threadfence_system();
         }
         xch_ok_s = ok;
     }
@@ -76,15 +90,15 @@ FLIP_D void xch_leave(const Xch &X, bool remote_stores) {
     if (X.nranks == 1) return;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (remote_stores) __threadfence_system();
+        if (remote_stores) xch_fence();       // release: this CTA's peer stores are performed before its arrival is counted
         unsigned int prev = atomicAdd(&X.local->cta_done, 1u);
         if (prev == gridDim.x - 1) {
+            if (remote_stores) xch_fence();   // acquire the other CTAs' arrivals, release the flag stores below
             X.local->cta_done = 0;
             unsigned long long n = X.local->done + 1;
             X.local->done = n;
-            __threadfence_system();
             for (int p = 0; p < X.nranks; p++)
-                if (p != X.rank) ((volatile unsigned long long *)X.peers[p]->arrive)[X.rank] = n;
+                if (p != X.rank) xch_st_relaxed(&((volatile unsigned long long *)X.peers[p]->arrive)[X.rank], n);
         }
     }
 }
