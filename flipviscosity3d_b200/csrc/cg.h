@@ -55,17 +55,49 @@ FLIP_D double reduce_partials(const double *__restrict__ part, int n, double *sm
     return cta_reduce<MAX>(v, sm);
 }
 
-// Partials of reduction `kind` live at part[kind * nranks * G ...): G slots per rank, rank-major.  The producing CTA
-// stores its value into EVERY rank's array (one 8-byte NVLink store per peer), consumers re-reduce all nranks * G values
-// in that fixed order: bit-identical scalars on every rank, no all-reduce kernel.
-#define PART_STORE(P, kind, value)                                                                         \
-    do {                                                                                                   \
-        const size_t _o = ((size_t)(kind) * (P).X.nranks + (P).X.rank) * gridDim.x + blockIdx.x;           \
-        if ((P).X.nranks == 1) (P).part[_o] = (value);                                                     \
-        else for (int _p = 0; _p < (P).X.nranks; _p++) ((volatile double *)(P).part_peers[_p])[_o] = (value); \
-    } while (0)
+// Partials of reduction `kind` live at part[kind * nranks * G ...): G slots per rank, rank-major.  Every CTA stores its
+// value into its own rank's slots; on a sharded handle the LAST CTA of the kernel then copies the rank's slots to every
+// peer (PART_LEAVE: one coalesced burst and ONE system-scope fence per kernel - a fence in each of ~300 CTAs costs ~10 us,
+// measured) and posts the hand-shake.  Consumers re-reduce all nranks * G values in that fixed order: bit-identical
+// scalars on every rank, no all-reduce kernel.
+#define PART_KINDS 6
+#define PART_STORE(P, kind, value) (P).part[((size_t)(kind) * (P).X.nranks + (P).X.rank) * gridDim.x + blockIdx.x] = (value)
 #define PART_PTR(P, kind) ((P).part + (size_t)(kind) * (P).X.nranks * gridDim.x)
 #define PART_N(P) ((P).X.nranks * (int)gridDim.x)
+
+// end of a kernel that produced partials (all threads of every CTA): replaces xch_leave
+FLIP_D void part_leave(const Xch &X, double *part, double *const *part_peers) {
+    if (X.nranks == 1) return;
+    __shared__ int part_last_s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                  // this CTA's partials before its arrival (device scope)
+        unsigned int prev = atomicAdd(&X.local->cta_done, 1u);
+        part_last_s = prev == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!part_last_s) return;
+    __threadfence();
+    const int G = gridDim.x;
+    for (int kind = 0; kind < PART_KINDS; kind++) {       // all kinds: re-sending an unchanged value is harmless
+        const size_t o = ((size_t)kind * X.nranks + X.rank) * G;
+        for (int q = threadIdx.x; q < G; q += blockDim.x) {
+            const double v = ((volatile double *)part)[o + q];
+            for (int p = 0; p < X.nranks; p++)
+                if (p != X.rank) part_peers[p][o + q] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xch_fence();                                      // the copies are performed before the flags
+        X.local->cta_done = 0;
+        unsigned long long n = X.local->done + 1;
+        X.local->done = n;
+        for (int p = 0; p < X.nranks; p++)
+            if (p != X.rank) xch_st_relaxed(&((volatile unsigned long long *)X.peers[p]->arrive)[X.rank], n);
+    }
+}
+#define PART_LEAVE(P) part_leave((P).X, (P).part, (P).part_peers)
 
 struct CGParams {
     Grid g;
@@ -123,7 +155,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init(CGParams P, Diag diag, d
         if (!KEEPX) PART_STORE(P, 2, bm);
         else PART_STORE(P, 3, bm);   // max|r0|, informational
     }
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 // max|b| partials only (warm start: the relative tolerance refers to b, not to r0)
@@ -141,7 +173,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_bmax(CGParams P, Diag diag) {
     }
     bm = cta_reduce<true>(bm, sm);
     if (threadIdx.x == 0) PART_STORE(P, 2, bm);
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 // Warm start (x0 != 0): k_cg_guess puts the guess into s (so the phase-A kernel computes q = A x0),
@@ -245,7 +277,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_update(CGParams P, Diag diag,
         if (!MG) PART_STORE(P, 1, rz);
         PART_STORE(P, 2, rm);
     }
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 // multigrid mode: partials of r.z after the V-cycle
@@ -275,7 +307,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dot(CGParams P, Diag diag, in
         PART_STORE(P, 1, rz);
         if (flex) PART_STORE(P, 3, qz);
     }
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 // multigrid mode, start-up: x = 0, r = masked b, partial max|b|   (then V-cycle, k_cg_dot, k_cg_start)
@@ -300,7 +332,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_init_mg(CGParams P, Diag diag
     }
     bm = cta_reduce<true>(bm, sm);
     if (threadIdx.x == 0) PART_STORE(P, (KEEPX ? 3 : 2), bm);
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 template <int NC>
@@ -722,7 +754,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_init(CG2Params Q, Diag diag)
         PART_STORE(P, 1, gam);       // gamma(0)
         PART_STORE(P, 2, bm);        // rmax(0) = max|b|
     }
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 template <int NC, class Diag>
@@ -791,7 +823,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg2_step(CG2Params Q, Diag diag,
     gnew = cta_reduce<false>(gnew, sm);
     rm = cta_reduce<true>(rm, sm);
     if (threadIdx.x == 0) { PART_STORE(P, parity ? 1 : 3, gnew); PART_STORE(P, parity ? 2 : 4, rm); }
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 // `apply_uw(parity)` must launch the phase-A kernel on a CGParams whose s is u (P.z) and q is w: it computes w = A u and

@@ -137,16 +137,18 @@ static PushDesc push_desc(Sim &s, const Grid &g, void *field, size_t elem, int n
     return d;
 }
 
-static int push_grid(Sim &s, size_t bytes) {
-    long long ctas = (long long)(bytes / (256 * 16 * 2)) + 1;
-    long long cap = (long long)s.num_sms * 2;
+// CTAs of a push: every CTA ends with one system-scope fence (~microseconds when hundreds of CTAs do it, measured), so
+// a push uses few, fat CTAs: 32 KB per CTA, at most 64 of them for ghost planes and 4 per SM for bulk gathers.
+static int push_grid(Sim &s, size_t bytes, bool bulk) {
+    long long ctas = (long long)(bytes / (32 << 10)) + 1;
+    long long cap = bulk ? (long long)s.num_sms * 4 : 64;
     return (int)(ctas < cap ? ctas : cap);
 }
 
 void xch_push_halo(Sim &s, const Grid &g, void *field, size_t elem, int ncomp, int level, int halo) {
     if (!s.sharded) return;
     PushDesc d = push_desc(s, g, field, elem, ncomp, level, halo);
-    int G = push_grid(s, 2 * (size_t)halo * ncomp * d.plane_bytes);
+    int G = push_grid(s, 2 * (size_t)halo * ncomp * d.plane_bytes, false);
     FLIP_LAUNCH_SYNC(k_push_planes, G, 256, s.stream, xch_of(s), (const Cuts *)s.cuts, d);
     s.kernel_launches++;
 }
@@ -155,7 +157,7 @@ void xch_push_gather(Sim &s, const Grid &g, void *field, size_t elem, int ncomp,
     if (!s.sharded) return;
     PushDesc d = push_desc(s, g, field, elem, ncomp, level, 0);
     // a slab is at most the whole field; the usual one is 1/nranks of it
-    int G = push_grid(s, (size_t)ncomp * d.comp_stride_bytes / s.nranks * (s.nranks - 1));
+    int G = push_grid(s, (size_t)ncomp * d.comp_stride_bytes / s.nranks * (s.nranks - 1), true);
     FLIP_LAUNCH_SYNC(k_push_planes, G, 256, s.stream, xch_of(s), (const Cuts *)s.cuts, d);
     s.kernel_launches++;
 }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const
     }
     sq = cta_reduce<false>(sq, sm);
     if (threadIdx.x == 0) PART_STORE(P, 0, sq);
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 __global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const double *__restrict__ x, float *__restrict__ pr) {

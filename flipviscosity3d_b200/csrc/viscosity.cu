@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_visc_apply(CGParams P, const flo
     }
     sq = cta_reduce<false>(sq, sm);
     if (threadIdx.x == 0) PART_STORE(P, 0, sq);
-    xch_leave(P.X, true);
+    PART_LEAVE(P);
 }
 
 static void gmg_free(Sim &s);

@@ -62,7 +62,7 @@ def _scene_setup(n, viscosity):
     return setup
 
 
-@pytest.mark.parametrize("nranks", [2, 3])
+@pytest.mark.parametrize("nranks", [2, 3, 4])
 def test_sharded_frames_match_single_rank(emu_lib, nranks):
     n = 16
     setup = _scene_setup(n, 2.0)
