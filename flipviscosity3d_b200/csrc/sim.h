@@ -145,8 +145,8 @@ struct Sim {
     // A CG solve is only cut into slabs when it is big enough to pay for its per-kernel hand-shakes (a few microseconds
     // each, three per pressure iteration): below this many unknowns (whole system; decided from the previous solve so that
     // every rank takes the same branch) every rank runs the pressure solve in full on its own copy.  Measured on 2 B200:
-    // 0.62 M unknowns, 9.4 ms replicated vs 24 ms sharded.
-    long long shard_min_unknowns = 1500000;
+    // 0.62 M unknowns, 9.4 ms replicated vs 22 ms sharded; 8 ranks, 2.0 M unknowns (sheet 512^3), 12 ms vs 15 ms.
+    long long shard_min_unknowns = 8000000;
     int pres_last_unknowns = 0;
     double xch_timeout_s = 20.0;        // a rank that waits longer than this for its peers gives up (Link::status)
     int *xch_status_host = 0;           // pinned copy of Link::status, fetched with every convergence poll
