@@ -65,6 +65,9 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s, s.vcoef, 4 * T);
     dev_alloc(s, s.vdiag, 3 * T);
     dev_alloc(s, s.vmass, 3 * T);
+    dev_alloc(s, s.grid_flag0, (size_t)g.nblocks); dev_alloc(s, s.grid_flag, (size_t)g.nblocks);
+    dev_alloc(s, s.grid_dirty, (size_t)g.nblocks); dev_alloc(s, s.grid_dirty_next, (size_t)g.nblocks);
+    dev_alloc(s, s.grid_list, (size_t)g.nblocks); dev_alloc(s, s.grid_count, 1);
     dev_alloc(s, s.ext_flag, (size_t)g.nblocks); dev_alloc(s, s.ext_flag2, (size_t)g.nblocks);
     dev_alloc(s, s.ext_list, (size_t)g.nblocks); dev_alloc(s, s.ext_count, 1);
     dev_alloc(s, s.blk_flag, (size_t)g.nblocks);
@@ -211,6 +214,7 @@ static void upload_field(Sim &s, const FieldRef &r, const float *in) {
     auto kern = &k_unpack<float>;
     FLIP_LAUNCH(kern, cdiv((long long)n, 256), 256, s.stream, s.g, (const float *)staging(s), r.ptr, r.w, r.h, r.d);
     KERNEL_CHECK();
+    grid_list_mark_all_dirty(s);   // the caller may have put data anywhere: the next block lists cover the whole grid once
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
 }
 static void download_field(Sim &s, const FieldRef &r, float *out) {
@@ -242,6 +246,7 @@ void sim_substep(Sim &s, float dt) {
     stage_constrain(s);
     CUDA_CHECK(cudaEventRecord(ev[6], s.stream));
     stage_advect_particles(s, dt);
+    grid_list_end_substep(s, true);
     CUDA_CHECK(cudaEventRecord(ev[7], s.stream));
     CUDA_CHECK(cudaEventSynchronize(ev[7]));
     for (int i = 0; i < 7; i++) CUDA_CHECK(cudaEventElapsedTime(&s.stage_ms[i], ev[i], ev[i + 1]));
@@ -305,6 +310,10 @@ int flip_create(int ni, int nj, int nk, float dx, flip_sim **out) {
                     nj + 1, nk + 1, 1.0f);
         FLIP_LAUNCH(k_fill_box, cdiv((long long)(ni + 1) * (nj + 1) * (nk + 1), 256), 256, s.stream, g, s.phi_sol, ni + 1,
                     nj + 1, nk + 1, (float)(ni + nj + nk) * dx);
+        // defaults of the fields the grid stages only rewrite near the liquid (fields.cu, near-liquid block list):
+        // liquid SDF = its "no particle in reach" value 3 dx (src/particlelevelset.cpp:94-96), extrapolation layer = unknown
+        FLIP_LAUNCH(k_fill_box, cdiv((long long)ni * nj * nk, 256), 256, s.stream, g, s.phi_liq, ni, nj, nk, 3.0f * dx);
+        CUDA_CHECK(cudaMemsetAsync(s.layer, 0xFF, 3 * (size_t)g.total, s.stream));
         KERNEL_CHECK();
         solid_precompute(s);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -437,6 +446,7 @@ int flip_set_viscosity_uniform(flip_sim *h, float v) {
                 g.ni + 1, g.nj + 1, g.nk + 1, v);
     KERNEL_CHECK();
     s.viscosity_nonzero = v > 0.0f;
+    grid_list_mark_all_dirty(s);   // the viscosity-derived fields are only maintained while there is viscosity
     API_END()
 }
 
@@ -452,7 +462,7 @@ int flip_set_viscosity_grid(flip_sim *h, const float *v) {
     }
     FieldRef r;
     field_ref(s, FLIP_F_VISCOSITY, r);
-    upload_field(s, r, v);
+    upload_field(s, r, v);   // (marks every block dirty)
     s.viscosity_nonzero = nonzero;
     API_END()
 }
@@ -554,6 +564,7 @@ int flip_set_valid(flip_sim *h, int comp, const uint8_t *in) {
     auto kern = &k_unpack<unsigned char>;
     FLIP_LAUNCH(kern, cdiv((long long)n, 256), 256, s.stream, g, (const unsigned char *)stage, s.valid + (size_t)comp * g.total, w, hh, d);
     KERNEL_CHECK();
+    grid_list_mark_all_dirty(s);
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     API_END()
 }
@@ -595,6 +606,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_sweeps_l1") s.mg_sweeps_l1 = (int)value;
     else if (n == "pic_ratio") s.pic_ratio = (float)value;
     else if (n == "cfl") { s.cfl_number = (float)value; s.extrap_layers = (int)ceil(s.cfl_number) + 2; }
+    else if (n == "use_block_lists") { s.use_block_lists = (int)value; s.world_epoch++; }
     else if (n == "verbose") s.verbose = (int)value;
     else return fail_inval(s, "flip_set_param: unknown parameter name");
     return FLIP_OK;

@@ -32,6 +32,14 @@ FLIP_D BlockCell block_cell(const Grid &g, int blk, int t) {
     return c;
 }
 
+// Grid stages run over the list of 8x8x8 blocks near the liquid (fields.cu grid_list_ensure) instead of the dense grid:
+// one CTA of CG_THREADS threads per listed block, thread = cell.  The body sees (i, j, k) of a cell inside
+// [0, ni] x [0, nj] x [0, nk] exactly like the dense (n+1)^3 sweeps it replaces; `continue` leaves the cell.
+#define FOR_LIST_CELLS(g, glist, gcount, i, j, k)                                                        \
+    for (int _b = blockIdx.x, _nb = *(gcount); _b < _nb; _b += gridDim.x)                                \
+        for (BlockCell _c = block_cell(g, (glist)[_b], threadIdx.x); _c.inside; _c.inside = false)      \
+            for (int i = _c.i, j = _c.j, k = _c.k, _once = 1; _once; _once = 0)
+
 // sum (or max) over the CTA; result valid in every thread
 template <bool MAX>
 FLIP_D double cta_reduce(double v, double *sm /*[CG_THREADS/32]*/) {
@@ -568,6 +576,11 @@ __global__ void __launch_bounds__(CG_THREADS) k_cell_fill(Grid g, const int *__r
         int rank = before + __popc(bal & ((1u << lane) - 1u));
         if (has) cells[offset[b] + rank] = id;
     }
+}
+
+static inline int list_grid(const Sim &s) {   // CTAs of a kernel over the near-liquid block list
+    int gsz = s.num_sms * 4;
+    return gsz > s.g.nblocks ? s.g.nblocks : gsz;
 }
 
 static inline int cg_grid(const Sim &s) {

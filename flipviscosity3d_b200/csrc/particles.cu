@@ -10,7 +10,7 @@
 // both scatters of the reference (min-scatter for the SDF, Wyvill-weighted add-scatter for P2G)
 // become GATHERS over contiguous particle runs: no atomics, bit-reproducible run to run, and a
 // k-slab decomposition only needs one ghost layer of particles instead of a halo-add.
-#include "sim.h"
+#include "cg.h"
 #include "scan.h"
 
 // ------------------------------------------------------------------------------------------
@@ -85,6 +85,7 @@ void bin_particles(Sim &s) {
     }
     KERNEL_CHECK();
     s.binned = true;
+    s.world_epoch++;   // the cell occupancy the block list is built from is new
 }
 
 // ------------------------------------------------------------------------------------------
@@ -92,11 +93,12 @@ void bin_particles(Sim &s) {
 // then phi = -dx/2 where phi < dx/2 inside the solid.   (src/particlelevelset.cpp:98-139)
 // min is exact and order independent, so this gather is bit-identical to the reference scatter.
 // ------------------------------------------------------------------------------------------
-__global__ void k_liquid_sdf(Grid g, const float *__restrict__ px, const float *__restrict__ py,
+__global__ void __launch_bounds__(CG_THREADS) k_liquid_sdf(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount,
+                             const float *__restrict__ px, const float *__restrict__ py,
                              const float *__restrict__ pz, const int *__restrict__ cell_start,
                              const float *__restrict__ sol_center, float *__restrict__ phi, float radius) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni, g.nj, g.nk, i, j, k)) return;
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
+    if (i >= g.ni || j >= g.nj || k >= g.nk) continue;
     float cx = index_to_center(i, g.dxd), cy = index_to_center(j, g.dxd), cz = index_to_center(k, g.dxd);
     float best = 3.0f * g.dx;  // ParticleLevelSet::_getMaxDistance (src/particlelevelset.cpp:94-96)
     int i0 = max(i - 1, 0), i1 = min(i + 1, g.ni - 1);
@@ -114,18 +116,20 @@ __global__ void k_liquid_sdf(Grid g, const float *__restrict__ px, const float *
     // _extrapolateSignedDistanceIntoSolids (src/particlelevelset.cpp:127-139)
     if ((double)best < 0.5 * g.dxd && sol_center[id] < 0.0f) best = -0.5f * g.dx;
     phi[id] = best;
+  }
 }
 
 void stage_update_liquid_sdf(Sim &s) {
     bin_particles(s);
     const Grid &g = s.g;
     int c = s.cur;
-    long long n = (long long)g.ni * g.nj * g.nk;
-    FLIP_LAUNCH(k_liquid_sdf, cdiv(n, 256), 256, s.stream, g, (const float *)s.p[c][0], (const float *)s.p[c][1],
-                (const float *)s.p[c][2], (const int *)s.cell_start, (const float *)s.sol_center, s.phi_liq,
-                s.particle_radius);
+    grid_list_ensure(s);   // blocks within one block of a particle (or of last substep's liquid): elsewhere phi stays 3 dx
+    FLIP_LAUNCH(k_liquid_sdf, list_grid(s), CG_THREADS, s.stream, g, (const int *)s.grid_list, (const int *)s.grid_count,
+                (const float *)s.p[c][0], (const float *)s.p[c][1], (const float *)s.p[c][2], (const int *)s.cell_start,
+                (const float *)s.sol_center, s.phi_liq, s.particle_radius);
     s.kernel_launches++;
     KERNEL_CHECK();
+    s.world_epoch++;       // the liquid SDF changed
 }
 
 // ------------------------------------------------------------------------------------------
@@ -178,17 +182,18 @@ FLIP_D void p2g_face(const Grid &g, const float *__restrict__ px, const float *_
     valid[id] = ok;
 }
 
-__global__ void __launch_bounds__(256) k_p2g(Grid g, const float *__restrict__ px, const float *__restrict__ py,
+__global__ void __launch_bounds__(CG_THREADS) k_p2g(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount,
+                                             const float *__restrict__ px, const float *__restrict__ py,
                                              const float *__restrict__ pz, const float *__restrict__ vx,
                                              const float *__restrict__ vy, const float *__restrict__ vz,
                                              const int *__restrict__ cell_start, const float *__restrict__ phi,
                                              Wyvill wy, float *__restrict__ vel, unsigned char *__restrict__ valid) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
-    size_t T = (size_t)g.total;
-    if (j < g.nj && k < g.nk) p2g_face<0>(g, px, py, pz, vx, cell_start, phi, wy, i, j, k, vel, valid);
-    if (i < g.ni && k < g.nk) p2g_face<1>(g, px, py, pz, vy, cell_start, phi, wy, i, j, k, vel + T, valid + T);
-    if (i < g.ni && j < g.nj) p2g_face<2>(g, px, py, pz, vz, cell_start, phi, wy, i, j, k, vel + 2 * T, valid + 2 * T);
+    FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
+        size_t T = (size_t)g.total;
+        if (j < g.nj && k < g.nk) p2g_face<0>(g, px, py, pz, vx, cell_start, phi, wy, i, j, k, vel, valid);
+        if (i < g.ni && k < g.nk) p2g_face<1>(g, px, py, pz, vy, cell_start, phi, wy, i, j, k, vel + T, valid + T);
+        if (i < g.ni && j < g.nj) p2g_face<2>(g, px, py, pz, vz, cell_start, phi, wy, i, j, k, vel + 2 * T, valid + 2 * T);
+    }
 }
 
 void stage_advect_velocity_field(Sim &s) {
@@ -202,8 +207,9 @@ void stage_advect_velocity_field(Sim &s) {
     wy.c1 = (4.0f / 9.0f) * (1.0f / (r * r * r * r * r * r));
     wy.c2 = (17.0f / 9.0f) * (1.0f / (r * r * r * r));
     wy.c3 = (22.0f / 9.0f) * (1.0f / (r * r));
-    long long n = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
-    FLIP_LAUNCH(k_p2g, cdiv(n, 256), 256, s.stream, g, (const float *)s.p[c][0], (const float *)s.p[c][1],
+    grid_list_ensure(s);
+    FLIP_LAUNCH(k_p2g, list_grid(s), CG_THREADS, s.stream, g, (const int *)s.grid_list, (const int *)s.grid_count,
+                (const float *)s.p[c][0], (const float *)s.p[c][1],
                 (const float *)s.p[c][2], (const float *)s.p[c][3], (const float *)s.p[c][4], (const float *)s.p[c][5],
                 (const int *)s.cell_start, (const float *)s.phi_liq, wy, s.vel, s.valid);
     s.kernel_launches++;

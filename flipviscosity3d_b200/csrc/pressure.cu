@@ -14,11 +14,11 @@
 #include "levelset_math.h"
 
 // rhs (into r) and stencil coefficients for every cell; non-unknown cells get zeros.
-__global__ void __launch_bounds__(256) k_pressure_build(Grid g, const float *__restrict__ phi, const float *__restrict__ vel,
+__global__ void __launch_bounds__(CG_THREADS) k_pressure_build(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount,
+                                                        const float *__restrict__ phi, const float *__restrict__ vel,
                                                         const float *__restrict__ weight, float4 *__restrict__ coef,
                                                         double *__restrict__ rhs, float scale, float minfrac) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
     size_t T = (size_t)g.total;
     float4 c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) k_pressure_build(Grid g, const float *__r
     }
     coef[id] = c;
     rhs[id] = b;
+  }
 }
 
 // phase A: q = A s on the active blocks (row order of src/pressuresolver.cpp:464-499) and s.q partials
@@ -98,11 +99,13 @@ __global__ void __launch_bounds__(CG_THREADS) k_pressure_apply(CGParams P, const
     PART_LEAVE(P);
 }
 
-__global__ void k_pressure_store(Grid g, const float4 *__restrict__ coef, const double *__restrict__ x, float *__restrict__ pr) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni, g.nj, g.nk, i, j, k)) return;
-    int id = gidx(g, i, j, k);
-    pr[id] = coef[id].x != 0.0f ? (float)x[id] : 0.0f;
+__global__ void __launch_bounds__(CG_THREADS) k_pressure_store(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount,
+                                                                const float4 *__restrict__ coef, const double *__restrict__ x, float *__restrict__ pr) {
+    FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
+        if (i >= g.ni || j >= g.nj || k >= g.nk) continue;
+        int id = gidx(g, i, j, k);
+        pr[id] = coef[id].x != 0.0f ? (float)x[id] : 0.0f;
+    }
 }
 
 void solve_pressure(Sim &s, float dt) {
@@ -115,9 +118,9 @@ void solve_pressure(Sim &s, float dt) {
     xch_update_cuts(s);   // k-slabs balanced by liquid cells (no-op on one GPU)
     // scale = deltaTime / (dx*dx) in double, used as (float)scale (src/pressuresolver.cpp:250, 259)
     double scale = (double)dt / (g.dxd * g.dxd);
-    long long nf = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
-    FLIP_LAUNCH(k_pressure_build, cdiv(nf, 256), 256, s.stream, g, (const float *)s.phi_liq, (const float *)s.vel,
-                (const float *)s.weight, s.pcoef, s.cg_r, (float)scale, s.minfrac);
+    grid_list_ensure(s);
+    FLIP_LAUNCH(k_pressure_build, list_grid(s), CG_THREADS, s.stream, g, (const int *)s.grid_list, (const int *)s.grid_count,
+                (const float *)s.phi_liq, (const float *)s.vel, (const float *)s.weight, s.pcoef, s.cg_r, (float)scale, s.minfrac);
     s.kernel_launches++;
     DiagPressure diag{s.pcoef};
     build_block_list<1>(s, diag);
@@ -151,8 +154,8 @@ void solve_pressure(Sim &s, float dt) {
     xch_barrier(s);
     CUDA_CHECK(cudaStreamSynchronize(s.stream));
     xch_check(s);
-    long long nc = (long long)g.ni * g.nj * g.nk;
-    FLIP_LAUNCH(k_pressure_store, cdiv(nc, 256), 256, s.stream, g, (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);
+    FLIP_LAUNCH(k_pressure_store, list_grid(s), CG_THREADS, s.stream, g, (const int *)s.grid_list, (const int *)s.grid_count,
+                (const float4 *)s.pcoef, (const double *)s.cg_x, s.pressure);
     s.kernel_launches++;
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.blk_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));

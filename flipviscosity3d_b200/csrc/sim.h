@@ -117,6 +117,11 @@ struct Sim {
     float *vcoef = 0;         // 4 coefficient grids [4*total]: center, edgeU, edgeV, edgeW
     float *vdiag = 0;         // [3*total] row diagonals (0 = not an unknown)
     float *vmass = 0;         // [3*total] mass term of every row as the CG operator applies it (viscosity.cu k_visc_rows)
+    // near-liquid block list of the grid stages (fields.cu grid_list_ensure): blocks within one block of a particle or a
+    // liquid cell, plus the blocks that were in the list during the previous substep (their fields go back to defaults)
+    int *grid_flag0 = 0, *grid_flag = 0, *grid_dirty = 0, *grid_dirty_next = 0, *grid_list = 0, *grid_count = 0;   // [nblocks] x5, [1]
+    unsigned long long world_epoch = 1, grid_list_epoch = 0;   // particles / liquid SDF changed <-> list built for
+    int use_block_lists = 1;   // 0: every grid stage sweeps all blocks (debug / A-B timing)
     int *ext_flag = 0, *ext_flag2 = 0, *ext_list = 0, *ext_count = 0;   // extrapolation block list [nblocks] x3, [1]
     int *blk_flag = 0;        // [nblocks]
     int *blk_list = 0;        // [nblocks]
@@ -183,6 +188,9 @@ void sim_free(Sim &s);
 void sim_reserve_particles(Sim &s, long long n);
 
 // fields.cu
+void grid_list_ensure(Sim &s);               // (re)build the near-liquid block list if particles or the liquid SDF changed
+void grid_list_mark_all_dirty(Sim &s);       // a caller wrote arbitrary field data: next lists cover every block once
+void grid_list_end_substep(Sim &s, bool all_stages_ran);
 void solid_precompute(Sim &s);               // weights, cell-centre solid phi, face states
 void stage_add_body_force(Sim &s, float dt);
 void extrapolate_velocity(Sim &s);

@@ -40,9 +40,8 @@ __device__ __host__ inline VolGrid vol_grid(const Grid &g, int v) {
 
 // liquid cells dilated twice in 6-connectivity on the (ni+1)(nj+1)(nk+1) index box
 // (src/viscositysolver.cpp:138-168) = cells within L1 distance 2 of a cell with phi < 0
-__global__ void __launch_bounds__(256) k_visc_valid(Grid g, const float *__restrict__ phi, unsigned char *__restrict__ vvalid) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+__global__ void __launch_bounds__(CG_THREADS) k_visc_valid(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount, const float *__restrict__ phi, unsigned char *__restrict__ vvalid) {
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     bool v = false;
     for (int dk = -2; dk <= 2 && !v; dk++) {
         int rj = 2 - abs(dk);
@@ -58,6 +57,7 @@ __global__ void __launch_bounds__(256) k_visc_valid(Grid g, const float *__restr
         }
     }
     vvalid[gidx(g, i, j, k)] = v ? 1 : 0;
+  }
 }
 
 // nodal phi of the 7 control-volume families.  The reference caches node values first-come in
@@ -106,10 +106,9 @@ __global__ void __launch_bounds__(256) k_visc_nodes(Grid g, const float *__restr
     }
 }
 
-__global__ void __launch_bounds__(256) k_visc_volumes(Grid g, const unsigned char *__restrict__ vvalid,
+__global__ void __launch_bounds__(CG_THREADS) k_visc_volumes(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount, const unsigned char *__restrict__ vvalid,
                                                       const float *__restrict__ vnode, float *__restrict__ vvol) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
     bool valid = vvalid[id] != 0;
     for (int v = 0; v < 7; v++) {
@@ -126,24 +125,26 @@ __global__ void __launch_bounds__(256) k_visc_volumes(Grid g, const unsigned cha
         }
         vvol[(size_t)v * g.total + id] = out;
     }
+  }
 }
 
 void viscosity_volumes(Sim &s) {
     const Grid &g = s.g;
-    long long n1 = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
     long long n2 = (long long)(g.ni + 2) * (g.nj + 2) * (g.nk + 2);
-    FLIP_LAUNCH(k_visc_valid, cdiv(n1, 256), 256, s.stream, g, (const float *)s.phi_liq, s.vvalid);
+    grid_list_ensure(s);
+    const int *gl = s.grid_list, *gc = s.grid_count;
+    FLIP_LAUNCH(k_visc_valid, list_grid(s), CG_THREADS, s.stream, g, gl, gc, (const float *)s.phi_liq, s.vvalid);
+    // nodes: the index box is one wider than the blocks cover; the kernel leaves at once where no valid cell is near
     FLIP_LAUNCH(k_visc_nodes, cdiv(n2, 256), 256, s.stream, g, (const float *)s.phi_liq, (const unsigned char *)s.vvalid, s.vnode);
-    FLIP_LAUNCH(k_visc_volumes, cdiv(n1, 256), 256, s.stream, g, (const unsigned char *)s.vvalid, (const float *)s.vnode, s.vvol);
+    FLIP_LAUNCH(k_visc_volumes, list_grid(s), CG_THREADS, s.stream, g, gl, gc, (const unsigned char *)s.vvalid, (const float *)s.vnode, s.vvol);
     s.kernel_launches += 3;
     KERNEL_CHECK();
 }
 
 // coefficient fields: cc = 2*f*mu*vol_center, ceu/cev/cew = f*mu_bar*vol_edge{U,V,W}
-__global__ void __launch_bounds__(256) k_visc_coefs(Grid g, const float *__restrict__ visc, const float *__restrict__ vvol,
+__global__ void __launch_bounds__(CG_THREADS) k_visc_coefs(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount, const float *__restrict__ visc, const float *__restrict__ vvol,
                                                     float *__restrict__ vcoef, float factor) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
     size_t T = (size_t)g.total;
     float mu = visc[id];
@@ -156,17 +157,17 @@ __global__ void __launch_bounds__(256) k_visc_coefs(Grid g, const float *__restr
     vcoef[1 * T + id] = factor * mu_u * vvol[VEU * T + id];
     vcoef[2 * T + id] = factor * mu_v * vvol[VEV * T + id];
     vcoef[3 * T + id] = factor * mu_w * vvol[VEW * T + id];
+  }
 }
 
 // rows: unknown test, diagonal, rhs (rhs goes to r)
 // vmass = the mass term the CG operator uses for every row (see k_visc_apply): the face volume itself (exact == 1, the
 // default), or what is left of it in the reference's fp32 diagonal, d_fp32 - (sum of the six factors) (exact == 0).
-__global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restrict__ vvol, const float *__restrict__ vcoef,
+__global__ void __launch_bounds__(CG_THREADS) k_visc_rows(Grid g, const float *__restrict__ vvol, const float *__restrict__ vcoef,
                                                    const unsigned char *__restrict__ fstate, const float *__restrict__ vel,
                                                    float *__restrict__ vdiag, double *__restrict__ rhs, float *__restrict__ vmass,
-                                                   int exact) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+                                                   int exact, const int *__restrict__ glist, const int *__restrict__ gcount) {
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     int id = gidx(g, i, j, k), sy = SY(g), sz = SZ(g);
     size_t T = (size_t)g.total;
     const float *cc = vcoef, *cu = vcoef + T, *cv = vcoef + 2 * T, *cw = vcoef + 3 * T;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(256) k_visc_rows(Grid g, const float *__restri
     rhs[id] = dU != 0.0f ? bU : 0.0;
     rhs[T + id] = dV != 0.0f ? bV : 0.0;
     rhs[2 * T + id] = dW != 0.0f ? bW : 0.0;
+  }
 }
 
 // phase A: q = A s for the three face families of each cell index
@@ -713,9 +715,8 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
 }
 
 // _applySolutionToVelocityField: the whole field is cleared, unknowns get (float)soln
-__global__ void __launch_bounds__(256) k_visc_store(Grid g, const float *__restrict__ vdiag, const double *__restrict__ x, float *__restrict__ vel) {
-    int i, j, k;
-    if (!unflatten((long long)blockIdx.x * blockDim.x + threadIdx.x, g.ni + 1, g.nj + 1, g.nk + 1, i, j, k)) return;
+__global__ void __launch_bounds__(CG_THREADS) k_visc_store(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount, const float *__restrict__ vdiag, const double *__restrict__ x, float *__restrict__ vel) {
+  FOR_LIST_CELLS(g, glist, gcount, i, j, k) {
     int id = gidx(g, i, j, k);
     size_t T = (size_t)g.total;
     for (int c = 0; c < 3; c++) {
@@ -723,6 +724,7 @@ __global__ void __launch_bounds__(256) k_visc_store(Grid g, const float *__restr
         if (i >= w || j >= h || k >= d) continue;
         vel[c * T + id] = vdiag[c * T + id] != 0.0f ? (float)x[c * T + id] : 0.0f;
     }
+  }
 }
 
 void stage_apply_viscosity(Sim &s, float dt) {
@@ -738,9 +740,10 @@ void stage_apply_viscosity(Sim &s, float dt) {
     float invdx = 1.0f / g.dx;
     float factor = dt * invdx * invdx;
     long long n1 = (long long)(g.ni + 1) * (g.nj + 1) * (g.nk + 1);
-    FLIP_LAUNCH(k_visc_coefs, cdiv(n1, 256), 256, s.stream, g, (const float *)s.viscosity, (const float *)s.vvol, s.vcoef, factor);
-    FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, g, (const float *)s.vvol, (const float *)s.vcoef,
-                (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0);
+    const int *gl = s.grid_list, *gc = s.grid_count;   // built by viscosity_volumes
+    FLIP_LAUNCH(k_visc_coefs, list_grid(s), CG_THREADS, s.stream, g, gl, gc, (const float *)s.viscosity, (const float *)s.vvol, s.vcoef, factor);
+    FLIP_LAUNCH(k_visc_rows, list_grid(s), CG_THREADS, s.stream, g, (const float *)s.vvol, (const float *)s.vcoef,
+                (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0, gl, gc);
     s.kernel_launches += 2;
     DiagViscosity diag{s.vdiag, g.total};
     build_block_list<3>(s, diag);
@@ -782,7 +785,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     // acceptance rule of src/viscositysolver.cpp:676-689
     bool accept = !h.fail && (h.converged || (h.iter >= maxit && h.resid < s.visc_accept));
     if (accept) {
-        FLIP_LAUNCH(k_visc_store, cdiv(n1, 256), 256, s.stream, g, (const float *)s.vdiag, (const double *)s.cg_x, s.vel);
+        FLIP_LAUNCH(k_visc_store, list_grid(s), CG_THREADS, s.stream, g, gl, gc, (const float *)s.vdiag, (const double *)s.cg_x, s.vel);
         s.kernel_launches++;
     }
     KERNEL_CHECK();
@@ -827,8 +830,10 @@ extern "C" int flip_debug_visc_rhs(void *hsim, double *b_host, float *diag_host,
     // the rhs of the last solve is gone (r was consumed); recompute rows
     try {
         long long n1 = (long long)(s.g.ni + 1) * (s.g.nj + 1) * (s.g.nk + 1);
-        FLIP_LAUNCH(k_visc_rows, cdiv(n1, 256), 256, s.stream, s.g, (const float *)s.vvol, (const float *)s.vcoef,
-                    (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0);
+        grid_list_ensure(s);
+        FLIP_LAUNCH(k_visc_rows, list_grid(s), CG_THREADS, s.stream, s.g, (const float *)s.vvol, (const float *)s.vcoef,
+                    (const unsigned char *)s.fstate, (const float *)s.vel, s.vdiag, s.cg_r, s.vmass, s.visc_operator == 0 ? 1 : 0,
+                    (const int *)s.grid_list, (const int *)s.grid_count);
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
         CUDA_CHECK(cudaMemcpy(b_host, s.cg_r, 3 * T * sizeof(double), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(diag_host, s.vdiag, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
