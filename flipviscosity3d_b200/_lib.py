@@ -44,6 +44,8 @@ SYMBOLS = {
     "flip_mesh_sdf": (C.c_int, [_H, _FP, C.c_int, C.POINTER(C.c_int32), C.c_int, _FP]),
     "flip_srand": (C.c_int, [C.c_uint]),
     "flip_rand": (C.c_int, []),
+    "flip_get_positions_async": (C.c_int, [_H, _FP, C.c_int64, C.POINTER(C.c_int64)]),
+    "flip_output_wait": (C.c_int, [_H]),
     "flip_num_particles": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "flip_set_viscosity_uniform": (C.c_int, [_H, C.c_float]),
     "flip_set_viscosity_grid": (C.c_int, [_H, _FP]),

@@ -122,6 +122,12 @@ void sim_free(Sim &s) {
     // graphs may hold captured NCCL kernels: destroy them before the communicator
     for (int q = 0; q < 2; q++) if (s.cg_graph[q]) { cudaGraphExecDestroy((cudaGraphExec_t)s.cg_graph[q]); s.cg_graph[q] = 0; }
 #endif
+    if (s.out_stream) {
+        cudaStreamSynchronize((cudaStream_t)s.out_stream);
+        for (int q = 0; q < 2; q++) { if (s.out_buf[q]) cudaFree(s.out_buf[q]); cudaEventDestroy((cudaEvent_t)s.out_ready[q]); cudaEventDestroy((cudaEvent_t)s.out_done[q]); }
+        cudaStreamDestroy((cudaStream_t)s.out_stream);
+        s.out_stream = 0;
+    }
     for (int q = 0; q < 4; q++) if (s.user_ev[q]) { cudaEventDestroy((cudaEvent_t)s.user_ev[q]); s.user_ev[q] = 0; }
     try { dist_shutdown(s); } catch (...) {}
     viscosity_free(s);
@@ -432,6 +438,53 @@ int flip_mesh_sdf(flip_sim *h, const float *verts, int nv, const int *tris, int 
 int flip_srand(unsigned int seed) { scene_srand(seed); return FLIP_OK; }
 int flip_rand(void) { return scene_rand_next(); }
 
+// positions only, caller's order, 12 bytes per particle (what the reference's exporters write)
+__global__ void k_positions_out(float *__restrict__ xyz, const float *px, const float *py, const float *pz, const unsigned *pid, long long n) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    size_t o = 3 * (size_t)pid[t];
+    xyz[o] = px[t]; xyz[o + 1] = py[t]; xyz[o + 2] = pz[t];
+}
+
+int flip_get_positions_async(flip_sim *h, float *xyz_pinned, int64_t capacity, int64_t *n_out) {
+    API_BEGIN(h)
+    if (n_out) *n_out = s.np;
+    if (!xyz_pinned || capacity < s.np) return fail_inval(s, "flip_get_positions_async: null pointer or capacity too small");
+    if (s.np == 0) return FLIP_OK;
+    if (!s.out_stream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags((cudaStream_t *)&s.out_stream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; q++) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); s.out_ready[q] = (void *)e;
+                                      CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); s.out_done[q] = (void *)e; }
+    }
+    const int b = s.out_next;
+    s.out_next ^= 1;
+    if ((size_t)s.np > s.out_cap[b]) {
+        if (s.out_buf[b]) { CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)s.out_stream)); cudaFree(s.out_buf[b]); }
+        s.out_cap[b] = (size_t)s.np + (size_t)s.np / 8 + 1024;
+        CUDA_CHECK(cudaMalloc((void **)&s.out_buf[b], s.out_cap[b] * 3 * sizeof(float)));
+        s.out_used[b] = false;
+    }
+    // the staging buffer may still be draining from the export before last
+    if (s.out_used[b]) CUDA_CHECK(cudaStreamWaitEvent(s.stream, (cudaEvent_t)s.out_done[b], 0));
+    const int c = s.cur;
+    FLIP_LAUNCH(k_positions_out, cdiv(s.np, 256), 256, s.stream, s.out_buf[b], (const float *)s.p[c][0], (const float *)s.p[c][1],
+                (const float *)s.p[c][2], (const unsigned *)s.pid[c], s.np);
+    s.kernel_launches++;
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaEventRecord((cudaEvent_t)s.out_ready[b], s.stream));
+    CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)s.out_stream, (cudaEvent_t)s.out_ready[b], 0));
+    CUDA_CHECK(cudaMemcpyAsync(xyz_pinned, s.out_buf[b], (size_t)s.np * 3 * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)s.out_stream));
+    CUDA_CHECK(cudaEventRecord((cudaEvent_t)s.out_done[b], (cudaStream_t)s.out_stream));
+    s.out_used[b] = true;
+    API_END()
+}
+
+int flip_output_wait(flip_sim *h) {
+    API_BEGIN(h)
+    if (s.out_stream) CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)s.out_stream));
+    API_END()
+}
+
 int flip_num_particles(flip_sim *h, int64_t *n_out) {
     if (!h || !n_out) return FLIP_EINVAL;
     *n_out = h->s.np;
@@ -600,6 +653,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // unmap the peers: plain replicas again
     else if (n == "shard_min_unknowns") s.shard_min_unknowns = (long long)value;
     else if (n == "xch_timeout_s") s.xch_timeout_s = value;                    // takes effect at the next flip_dist_p2p_import
+    else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;

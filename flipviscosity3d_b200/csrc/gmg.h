@@ -524,6 +524,91 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
     xch_leave(L.X, false);
 }
 
+#ifndef FLIP_CPU_EMU
+// ---- the same sweep with the coefficient rows staged by TMA ---------------------------------------------------------
+// k_gmg_sweep is bound by L1 (ncu: l1tex 79 %): every row gathers 240 vector values through it, and its own 960-byte
+// coefficient row competes for the same cache.  Here lane 0 of every warp issues ONE bulk asynchronous copy
+// (cp.async.bulk global -> shared, completion counted in bytes on an mbarrier) per row, two rows in flight per warp, so the
+// coefficient stream goes L2 -> shared memory without touching L1 or the register file, and the gathers keep the cache.
+// Same arithmetic, same order: bit-identical to k_gmg_sweep.
+FLIP_D unsigned gmg_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+FLIP_D void gmg_bulk_load(float *dst_smem, const float *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gmg_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gmg_smem(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(gmg_smem(bar))
+                 : "memory");
+}
+FLIP_D void gmg_bar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GMG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GMG_DONE_%=;\n"
+        "bra GMG_WAIT_%=;\n"
+        "GMG_DONE_%=:\n"
+        "}\n" ::"r"(gmg_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int MODE>   // MODE 1 or 2
+__global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float *__restrict__ b, const float *__restrict__ xi,
+                                                        float *__restrict__ out, const float *__restrict__ pn, float omega,
+                                                        const CGState *__restrict__ st) {
+    __shared__ int offs[3][GMG_STRIDE];
+    __shared__ __align__(128) float Srow[8][2][GMG_STRIDE];
+    __shared__ __align__(8) unsigned long long bars[8][2];
+    if (st && st->done) return;
+    if (!xch_enter(L.X)) return;
+    for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(&bars[wid][0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(&bars[wid][1])) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy sees the initialised barriers
+    }
+    __syncthreads();
+    const int r0 = L.rng[0], r1 = L.rng[1];
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    int r = r0 + blockIdx.x * (blockDim.x >> 5) + wid;
+    unsigned phase[2] = {0u, 0u};
+    int buf = 0;
+    if (r < r1 && lane == 0) gmg_bulk_load(Srow[wid][0], L.S + (size_t)r * GMG_STRIDE, GMG_STRIDE * 4, &bars[wid][0]);
+    for (; r < r1; r += nwarps) {
+        const int rn = r + nwarps;
+        if (rn < r1 && lane == 0) gmg_bulk_load(Srow[wid][buf ^ 1], L.S + (size_t)rn * GMG_STRIDE, GMG_STRIDE * 4, &bars[wid][buf ^ 1]);
+        const int enc = L.rows[r];
+        const int m = enc / L.g.total, id = enc - m * L.g.total;
+        const float *__restrict__ xc = xi + id;
+        // the gathers do not depend on the coefficients: issue them before waiting for the row
+        float xv[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int slot = lane + 32 * t;
+            xv[t] = slot < GMG_STRIDE ? xc[offs[m][slot]] : 0.0f;
+        }
+        gmg_bar_wait(&bars[wid][buf], phase[buf]);
+        phase[buf] ^= 1u;
+        const float *Sr = Srow[wid][buf];
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int slot = lane + 32 * t;
+            if (slot < GMG_STRIDE) acc += Sr[slot] * xv[t];
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
+            else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
+        }
+        __syncwarp();   // every lane is done with this buffer before the copy after next overwrites it
+        buf ^= 1;
+    }
+    xch_leave(L.X, false);
+}
+#endif
+
 // ---- level 0 on the solver's compact cell list ------------------------------------------------
 // Same loads as k_visc_apply (viscosity.cu), in fp32: one thread per cell index that holds an unknown,
 // all three face rows at once.  MODE 0: x = omega b / d.  1: x = xi + omega (b - A xi) / d.

@@ -60,6 +60,7 @@ struct Sim {
     // coefficients per row, 8x fewer rows than level 0's matrix-free stencil): ONE sweep there and two everywhere
     // else costs no iterations (scipy prototype: 32 vs 31 at 128^3) and halves the level-1 traffic.
     int mg_sweeps_l0 = 3, mg_sweeps_l1 = 1;
+    int mg_tma = 1;                     // explicit-level sweeps stage their coefficient rows with TMA bulk copies (gmg.h)
     int mg_dense = 1;                   // exact dense solve on the first level with <= mg_dense_rows rows (else Jacobi sweeps there)
     int mg_dense_rows = 128;            // single-CTA Gauss-Jordan: 0.3 ms at 128 rows, 7 ms at 304 (measured) - keep it small
     int mg_chunk = 8;                   // multigrid CG iterations per graph replay / host convergence poll
@@ -156,6 +157,12 @@ struct Sim {
     double xch_timeout_s = 20.0;        // a rank that waits longer than this for its peers gives up (Link::status)
     int *xch_status_host = 0;           // pinned copy of Link::status, fetched with every convergence poll
 
+    // asynchronous position export (flip_get_positions_async): copy stream, two staging buffers, their events
+    void *out_stream = 0, *out_ready[2] = {0, 0}, *out_done[2] = {0, 0};
+    float *out_buf[2] = {0, 0};
+    size_t out_cap[2] = {0, 0};
+    bool out_used[2] = {false, false};
+    int out_next = 0;
     void *user_ev[4] = {0, 0, 0, 0};   // cudaEvent_t slots of flip_event_record (device-side timing for callers)
 
     // stats of the last substep

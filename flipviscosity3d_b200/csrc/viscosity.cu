@@ -519,7 +519,13 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
     const float w = M.omega;
     int cur[GMG_MAX_LEVELS];
     auto l0_first = &k_gmg0_sweep<0>; auto l0_smooth = &k_gmg0_sweep<1>; auto l0_resid = &k_gmg0_sweep<2>; auto l0_last = &k_gmg0_sweep<3>;
+#ifndef FLIP_CPU_EMU
+    // coefficient rows staged by TMA bulk copies (mg_tma, default) or read through L1 like the other operands
+    auto sweep1 = s.mg_tma ? &k_gmg_sweep_tma<1> : &k_gmg_sweep<1>;
+    auto sweep2 = s.mg_tma ? &k_gmg_sweep_tma<2> : &k_gmg_sweep<2>;
+#else
     auto sweep1 = &k_gmg_sweep<1>; auto sweep2 = &k_gmg_sweep<2>;
+#endif
     const int last = M.nlevels - 1;
     const bool sh = xch_cuts(s) != nullptr;
     GLevel &L0 = M.lv[0];
@@ -670,7 +676,7 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
         mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
-        mix(s.xch_epoch); mix((unsigned long long)s.sharded);
+        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
             mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
@@ -875,7 +881,11 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         if (!M || M->nlevels < 2 || M->lv[1].nrows == 0) return -1;
         GLevel &L = M->lv[1];
         GLevelDev D = gmg_dev(s, L, false);
+#ifndef FLIP_CPU_EMU
+        auto sweep1 = s.mg_tma ? &k_gmg_sweep_tma<1> : &k_gmg_sweep<1>;
+#else
         auto sweep1 = &k_gmg_sweep<1>;
+#endif
         int GR = gmg_row_grid(s, L);
         const float *nof = nullptr;
         FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[0], L.x[1], nof, M->omega, (const CGState *)nullptr);

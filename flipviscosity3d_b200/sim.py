@@ -120,6 +120,16 @@ class FlipSim:
     def srand(self, seed=1):
         self.lib.flip_srand(C.c_uint(seed))
 
+    def get_positions_async(self, out):
+        """start an asynchronous export of the positions into `out` ((n, 3) float32, ideally pinned); output_wait() completes it"""
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.ndim == 2 and out.shape[1] == 3
+        n = C.c_int64()
+        self._ck(self.lib.flip_get_positions_async(self.h, _fp(out), len(out), C.byref(n)))
+        return n.value
+
+    def output_wait(self):
+        self._ck(self.lib.flip_output_wait(self.h))
+
     def set_viscosity(self, v):
         if np.isscalar(v):
             self._ck(self.lib.flip_set_viscosity_uniform(self.h, C.c_float(v)))

@@ -95,6 +95,11 @@ int flip_set_solid_sdf(flip_sim *h, const float *phi_nodal);
 int flip_set_particles(flip_sim *h, const float *pos_vel_aos, int64_t n);
 int flip_get_particles(flip_sim *h, float *pos_vel_aos, int64_t capacity, int64_t *n_out);
 int flip_num_particles(flip_sim *h, int64_t *n_out);
+/* Output path (src/main.cpp:14-40 writes positions only): positions in the caller's order, 12 bytes per particle, copied to
+ * `xyz_pinned` (from flip_host_alloc) on a separate copy stream while the next substeps run; flip_output_wait blocks until
+ * every outstanding export has landed.  Two exports may be in flight. */
+int flip_get_positions_async(flip_sim *h, float *xyz_pinned, int64_t capacity, int64_t *n_out);
+int flip_output_wait(flip_sim *h);
 /* setViscosity(float) / setViscosity(Array3d<float>&) (src/fluidsimulation.cpp:99-124): v >= 0 */
 int flip_set_viscosity_uniform(flip_sim *h, float v);
 int flip_set_viscosity_grid(flip_sim *h, const float *v_nodesized);

@@ -271,6 +271,9 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0) {
     e->t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); return cudaSuccess;
 }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new EmuEvent(); return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->t - a->t) * 1e3); return cudaSuccess; }
 enum { cudaStreamNonBlocking = 1 };
 // "IPC" inside one process: the handle carries the pointer itself

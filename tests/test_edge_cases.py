@@ -177,3 +177,24 @@ def test_block_lists_equal_dense_sweeps(lib):
     assert st["viscosity_converged"] == 1 and st["pressure_converged"] == 1
     for sim in sims:
         sim.close()
+
+
+def test_async_position_export(lib):
+    """flip_get_positions_async / flip_output_wait: the positions the reference's exporters write (src/main.cpp:14-40), in
+    the caller's order, captured at the moment of the call while later substeps run"""
+    from __graft_entry__ import _analytic_scene
+    n = 16
+    phi, p = _analytic_scene(n)
+    sim = FlipSim(n, n, n, 1.0 / n, lib=lib)
+    sim.set_solid_sdf(phi); sim.set_particles(p); sim.set_viscosity(1.0)
+    bufs = [np.zeros((len(p), 3), np.float32) for _ in range(3)]
+    want = []
+    for f in range(3):
+        sim.advance(0.01)
+        want.append(sim.get_particles()[:, :3].copy())
+        assert sim.get_positions_async(bufs[f]) == len(p)     # three exports back to back: the third re-uses a staging buffer
+    sim.advance(0.01)                                          # keeps simulating while the copies drain
+    sim.output_wait()
+    for f in range(3):
+        assert np.array_equal(bufs[f], want[f])
+    sim.close()
