@@ -652,6 +652,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_chunk") s.mg_chunk = (int)value;
     else if (n == "dist_p2p") { if ((int)value == 0) dist_p2p_shutdown(s); }   // unmap the peers: plain replicas again
     else if (n == "shard_min_unknowns") s.shard_min_unknowns = (long long)value;
+    else if (n == "xch_nbr_wait") { s.xch_nbr_wait = (int)value; s.xch_epoch++; }
     else if (n == "xch_timeout_s") s.xch_timeout_s = value;                    // takes effect at the next flip_dist_p2p_import
     else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;

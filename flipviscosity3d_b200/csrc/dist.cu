@@ -113,6 +113,7 @@ Xch xch_of(Sim &s) {
     X.local = s.link; X.peers = s.link_peers;
     X.rank = s.sharded ? s.rank : 0;
     X.nranks = s.sharded ? s.nranks : 1;
+    X.nbr = s.xch_nbr_wait;
     return X;
 }
 const Cuts *xch_cuts(Sim &s) { return s.sharded ? s.cuts : nullptr; }

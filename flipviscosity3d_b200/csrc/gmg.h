@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
                                                     const CGState *__restrict__ st) {
     __shared__ int offs[3][GMG_STRIDE];
     if (st && st->done) return;
-    if (!xch_enter(L.X)) return;
+    if (!xch_enter(L.X, L.X.nbr != 0)) return;
     if (MODE != 0) {
         for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
         __syncthreads();
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     __shared__ __align__(128) float Srow[8][2][GMG_STRIDE];
     __shared__ __align__(8) unsigned long long bars[8][2];
     if (st && st->done) return;
-    if (!xch_enter(L.X)) return;
+    if (!xch_enter(L.X, L.X.nbr != 0)) return;
     for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
                                                      float *__restrict__ out, double *__restrict__ zout, float omega,
                                                      const CGState *__restrict__ st) {
     if (st && st->done) return;
-    if (MODE != 0 && !xch_enter(L.X)) return;   // mode 0 reads and writes this rank's own cells only
+    if (MODE != 0 && !xch_enter(L.X, L.X.nbr != 0)) return;   // mode 0 reads and writes this rank's own cells only
     const Grid &g = L.g;
     const int sy = SY(g), sz = SZ(g);
     const size_t T = (size_t)g.total;
@@ -715,7 +715,7 @@ FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float 
 __global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const float *__restrict__ xc, float *__restrict__ xf,
                                                        const CGState *__restrict__ st) {
     if (st && st->done) return;
-    if (!xch_enter(F.X)) return;
+    if (!xch_enter(F.X, F.X.nbr != 0)) return;
     const Grid &g = F.g;
     const size_t T = (size_t)g.total;
     const int nc = *F.cell_count;
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *_
 __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
                                                              float *__restrict__ x0, const CGState *__restrict__ st) {
     if (st && st->done) return;
-    if (!xch_enter(C.X)) return;
+    if (!xch_enter(C.X, C.X.nbr != 0)) return;
     const int r0 = C.rng[0], r1 = C.rng[1];
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);

@@ -154,6 +154,7 @@ struct Sim {
     // 0.62 M unknowns, 9.4 ms replicated vs 22 ms sharded; 8 ranks, 2.0 M unknowns (sheet 512^3), 12 ms vs 15 ms.
     long long shard_min_unknowns = 8000000;
     int pres_last_unknowns = 0;
+    int xch_nbr_wait = 0;               // 1: ghost-plane consumers wait for their two k-neighbours only (xch.h xch_enter); off until measured at N >= 4
     double xch_timeout_s = 20.0;        // a rank that waits longer than this for its peers gives up (Link::status)
     int *xch_status_host = 0;           // pinned copy of Link::status, fetched with every convergence poll
 

@@ -34,6 +34,7 @@ struct Xch {
     Link *local;
     Link *const *peers;   // device table [nranks]; peers[rank] == local
     int rank, nranks;     // nranks == 1: single GPU or replicas only - every call below is a no-op
+    int nbr;              // 1: kernels that only consume ghost planes wait for their two k-neighbours instead of all ranks
 };
 
 #ifdef FLIP_CPU_EMU
@@ -58,8 +59,12 @@ FLIP_D void xch_st_relaxed(volatile unsigned long long *p, unsigned long long v)
 FLIP_D void xch_fence() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 #endif
 
-// all threads of the CTA; false = the exchange is broken (time-out somewhere): return without doing anything
-FLIP_D bool xch_enter(const Xch &X) {
+// all threads of the CTA; false = the exchange is broken (time-out somewhere): return without doing anything.
+// nbr_only: wait for ranks rank-1 and rank+1 only.  Enough for a kernel that reads nothing remote but ghost planes: those
+// are stored by the neighbours, and the ghost planes this rank's next push overwrites are read by the neighbours.  Kernels
+// that read partials or gathered slabs (stored by everybody) wait for everybody; there are four of those per CG iteration,
+// so no rank ever runs more than a V-cycle ahead of any other.
+FLIP_D bool xch_enter(const Xch &X, bool nbr_only = false) {
     if (X.nranks == 1) return true;
     __shared__ int xch_ok_s;
     if (threadIdx.x == 0) {
@@ -70,7 +75,7 @@ FLIP_D bool xch_enter(const Xch &X) {
             const unsigned long long want = L->done;
             const long long t0 = clock64(), lim = L->timeout_cycles;
             for (int src = 0; src < X.nranks && ok; src++) {
-                if (src == X.rank) continue;
+                if (src == X.rank || (nbr_only && src != X.rank - 1 && src != X.rank + 1)) continue;
                 while (xch_ld_acquire(&L->arrive[src]) < want) {   // acquire: what the peer stored before its flag is visible
                     if (clock64() - t0 > lim) { L->status = 1; ok = 0; break; }
                     XCH_SPIN_PAUSE();
