@@ -424,7 +424,7 @@ def run_b200(args):
     barrier_sync()
     t0 = time.perf_counter()
     stage = np.zeros(8)
-    iters = {"p": 0, "v": 0, "p_ms": 0.0, "v_ms": 0.0, "p_unk": 0, "v_unk": 0}
+    iters = {"p": 0, "v": 0, "p_ms": 0.0, "v_ms": 0.0, "p_unk": 0, "v_unk": 0, "v_setup_ms": 0.0}
     dts, flags = [], []
     sim.event_record(0)
     for _ in range(args.steps):
@@ -433,6 +433,7 @@ def run_b200(args):
         stage += np.array(st["stage_ms"])
         iters["p"] += st["pressure_iterations"]; iters["v"] += st["viscosity_iterations"]
         iters["p_ms"] += st["pressure_solve_ms"]; iters["v_ms"] += st["viscosity_solve_ms"]
+        iters["v_setup_ms"] += st["viscosity_setup_ms"]
         iters["p_unk"] += st["pressure_unknowns"] * st["pressure_iterations"]
         iters["v_unk"] += st["viscosity_unknowns"] * st["viscosity_iterations"]
         flags.append((st["pressure_converged"], st["viscosity_converged"] if visc > 0 else 1,
@@ -580,6 +581,7 @@ def run_b200(args):
                          "unknowns": st1["pressure_unknowns"],
                          "cell_updates_per_s": iters["p_unk"] / (iters["p_ms"] * 1e-3) if iters["p_ms"] > 0 else None},
             "viscosity": {"iterations_per_step": iters["v"] / args.steps, "solve_ms_per_step": iters["v_ms"] / args.steps,
+                          "setup_ms_per_step": iters["v_setup_ms"] / args.steps,
                           "unknowns": st1["viscosity_unknowns"],
                           "cell_updates_per_s": iters["v_unk"] / (iters["v_ms"] * 1e-3) if iters["v_ms"] > 0 else None},
             "p2g_particles_per_s": len(p) / (stage[1] / args.steps * 1e-3) if stage[1] > 0 else None,

@@ -23,6 +23,7 @@ class flip_stats(C.Structure):
         ("stage_ms", C.c_float * 8),
         ("pressure_solve_ms", C.c_float), ("viscosity_solve_ms", C.c_float),
         ("pressure_unknowns", C.c_int64), ("viscosity_unknowns", C.c_int64),
+        ("viscosity_setup_ms", C.c_float), ("reserved2", C.c_float),
     ]
 
 

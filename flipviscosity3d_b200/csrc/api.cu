@@ -656,6 +656,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "xch_timeout_s") s.xch_timeout_s = value;                    // takes effect at the next flip_dist_p2p_import
     else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;
+    else if (n == "mg_build") s.mg_build = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;
     else if (n == "mg_sweeps_l1") s.mg_sweeps_l1 = (int)value;
@@ -690,6 +691,7 @@ int flip_get_stats(flip_sim *h, flip_stats *out) {
     for (int i = 0; i < 8; i++) out->stage_ms[i] = s.stage_ms[i];
     out->pressure_solve_ms = s.pres_stats.ms;
     out->viscosity_solve_ms = s.visc_stats.ms;
+    out->viscosity_setup_ms = s.visc_setup_ms;
     return FLIP_OK;
 }
 

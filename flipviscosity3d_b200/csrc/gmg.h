@@ -418,6 +418,129 @@ __global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build(Grid gc, Gri
     for (int q = lane; q < W.size; q += 32) S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc[q]);
 }
 
+// The same product in GATHER form (mg_build = 1, default).  Phase 1 is the scatter kernel's: t_j for every fine column of
+// the box, but kept in shared memory (fp64) instead of being scattered.  Phase 2: every lane owns output slots J and sums
+// t_j P[j,J] over the <= 48 children j of J, walking them in ascending column order - the order in which the scatter
+// kernel's lane-ordered steps reach a slot - so the two kernels are bit-identical (tests/test_gmg.py), without the
+// 32 serialised steps per 32 columns.
+#define GMG_TBOX_MAX 448   // columns of the box: children (<= 4 per axis) widened by the fine operator's reach (<= 2 each way)
+FLIP_D float gmg_child_weight(bool own, int q) {   // child q = 0..3 of a coarse index along one axis (fine index 2I-1+q)
+    return own ? (q == 1 ? 1.0f : (q < 3 ? 0.5f : 0.0f)) : ((q == 1 || q == 2) ? 0.75f : 0.25f);
+}
+template <bool FINE0>
+__global__ void __launch_bounds__(32 * GMG_BUILD_WARPS) k_gmg_build_g(Grid gc, Grid gf, const int *__restrict__ rows_c, const int *__restrict__ rng,
+                                                                       const float *__restrict__ diag_c, float *__restrict__ S_c,
+                                                                       const float *__restrict__ diag_f, const float *__restrict__ pn_f,
+                                                                       const float *__restrict__ coef_f, const int *__restrict__ rowmap_f,
+                                                                       const float *__restrict__ S_f, int nrows_f) {
+    __shared__ double t_s[GMG_BUILD_WARPS][GMG_TBOX_MAX];
+    __shared__ float wP_s[GMG_BUILD_WARPS][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int task = blockIdx.x * GMG_BUILD_WARPS + wid;        // (row of this rank's range, mp), mp fastest
+    const int r = rng[0] + task / 3, mp = task % 3;
+    if (r >= rng[1]) return;                                    // whole warp leaves together; no block-wide barrier below
+    if (rows_c[r] / gc.total > mp) return;                      // lower blocks are mirrored (k_gmg_mirror)
+    double *tb = t_s[wid];
+    float *wP = wP_s[wid];
+    const size_t Tc = (size_t)gc.total, Tf = (size_t)gf.total;
+    const int enc = rows_c[r];
+    const int m = enc / (int)Tc, idc = enc - m * (int)Tc;
+    int I, J, K;
+    gmg_unflatten(gc, idc, I, J, K);
+    const GWin W = gmg_window(m, mp);
+    const int sy = SY(gf), sz = SZ(gf);
+    const int lo[3] = {2 * I - 1, 2 * J - 1, 2 * K - 1};
+    const int cn[3] = {m == 0 ? 3 : 4, m == 1 ? 3 : 4, m == 2 ? 3 : 4};
+    const int nf[3] = {gf.ni, gf.nj, gf.nk};
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        int q = lane + 32 * t;
+        int a = q & 3, b2 = (q >> 2) & 3, c2 = q >> 4;
+        int fi = lo[0] + a, fj = lo[1] + b2, fk = lo[2] + c2;
+        float w = gmg_child_weight(m == 0, a) * gmg_child_weight(m == 1, b2) * gmg_child_weight(m == 2, c2);
+        if (w != 0.0f && fi >= 0 && fj >= 0 && fk >= 0 && fi <= nf[0] && fj <= nf[1] && fk <= nf[2]) {
+            size_t o = m * Tf + gidx(gf, fi, fj, fk);
+            float p = pn_f[o];
+            w = (diag_f[o] != 0.0f && p > 0.0f) ? w / p : 0.0f;
+        } else w = 0.0f;
+        wP[q] = w;
+    }
+    __syncwarp();
+    const GWin R = gmg_window(mp, m);
+    int olo[3], ohi[3], jlo[3], jn[3];
+    for (int a = 0; a < 3; a++) {
+        olo[a] = FINE0 ? -1 : R.lo[a];
+        ohi[a] = FINE0 ? 1 : R.lo[a] + R.n[a] - 1;
+        jlo[a] = lo[a] - ohi[a] < 0 ? 0 : lo[a] - ohi[a];
+        int jhi = lo[a] + cn[a] - 1 - olo[a] > nf[a] ? nf[a] : lo[a] + cn[a] - 1 - olo[a];
+        jn[a] = jhi - jlo[a] + 1;
+        if (jn[a] < 0) jn[a] = 0;
+    }
+    const int ncol = jn[0] * jn[1] * jn[2];
+    // ---- phase 1: t_j = sum_i P[i,I] A[i,j] / pn_j for every column of the box
+    for (int c = lane; c < ncol; c += 32) {
+        double t = 0.0;
+        const int ji = jlo[0] + c % jn[0], jj = jlo[1] + (c / jn[0]) % jn[1], jk = jlo[2] + c / (jn[0] * jn[1]);
+        const int idj = gidx(gf, ji, jj, jk);
+        const size_t oj = mp * Tf + idj;
+        float pnj = 0.0f;
+        if (diag_f[oj] != 0.0f) pnj = pn_f[oj];       // a column that is not an unknown drops out (pnj stays 0)
+        if (pnj != 0.0f) {
+            if (FINE0) {
+                int off[7][3];
+                double val[7];
+                int ne = gmg_entries_l0(mp, m, idj, sy, sz, Tf, coef_f, S_f /* level 0: the volume grids */, off, val);
+                for (int e = 0; e < ne; e++) {
+                    int a = ji + off[e][0] - lo[0], b2 = jj + off[e][1] - lo[1], c2 = jk + off[e][2] - lo[2];
+                    if (a < 0 || b2 < 0 || c2 < 0 || a >= cn[0] || b2 >= cn[1] || c2 >= cn[2]) continue;
+                    t += (double)wP[(c2 * 4 + b2) * 4 + a] * val[e];
+                }
+            } else {
+                const float *__restrict__ Sj = S_f + (size_t)rowmap_f[oj] * GMG_STRIDE + R.base;
+                int a0 = ji + olo[0] - lo[0], a1 = ji + ohi[0] - lo[0];
+                int b0 = jj + olo[1] - lo[1], b1 = jj + ohi[1] - lo[1];
+                int c0 = jk + olo[2] - lo[2], c1 = jk + ohi[2] - lo[2];
+                a0 = a0 < 0 ? 0 : a0; b0 = b0 < 0 ? 0 : b0; c0 = c0 < 0 ? 0 : c0;
+                a1 = a1 > cn[0] - 1 ? cn[0] - 1 : a1; b1 = b1 > cn[1] - 1 ? cn[1] - 1 : b1; c1 = c1 > cn[2] - 1 ? cn[2] - 1 : c1;
+                for (int c2 = c0; c2 <= c1; c2++)
+                    for (int b2 = b0; b2 <= b1; b2++) {
+                        const float *__restrict__ Sr = Sj + ((lo[2] + c2 - jk - R.lo[2]) * R.n[1] + (lo[1] + b2 - jj - R.lo[1])) * R.n[0] +
+                                                       (lo[0] - ji - R.lo[0]);
+                        for (int a = a0; a <= a1; a++) t += (double)wP[(c2 * 4 + b2) * 4 + a] * (double)Sr[a];
+                    }
+            }
+            t /= (double)pnj;
+        }
+        tb[c] = t;
+    }
+    __syncwarp();
+    // ---- phase 2: slot J = sum over the children j of J (component mp) of t_j P[j,J], ascending column order
+    for (int q = lane; q < W.size; q += 32) {
+        const int PI = I + W.lo[0] + q % W.n[0], PJ = J + W.lo[1] + (q / W.n[0]) % W.n[1], PK = K + W.lo[2] + q / (W.n[0] * W.n[1]);
+        double acc = 0.0;
+        if (PI >= 0 && PJ >= 0 && PK >= 0 && PI <= gc.ni && PJ <= gc.nj && PK <= gc.nk && diag_c[(size_t)mp * Tc + gidx(gc, PI, PJ, PK)] != 0.0f) {
+            for (int c2 = 0; c2 < 4; c2++) {
+                const float wk = gmg_child_weight(mp == 2, c2);
+                const int kk = 2 * PK - 1 + c2 - jlo[2];
+                if (wk == 0.0f || kk < 0 || kk >= jn[2]) continue;
+                for (int b2 = 0; b2 < 4; b2++) {
+                    const float wj = gmg_child_weight(mp == 1, b2);
+                    const int jj = 2 * PJ - 1 + b2 - jlo[1];
+                    if (wj == 0.0f || jj < 0 || jj >= jn[1]) continue;
+                    const double *__restrict__ trow = tb + (kk * jn[1] + jj) * jn[0];
+                    for (int a = 0; a < 4; a++) {
+                        const float wi = gmg_child_weight(mp == 0, a);
+                        const int ii = 2 * PI - 1 + a - jlo[0];
+                        if (wi == 0.0f || ii < 0 || ii >= jn[0]) continue;
+                        acc += trow[ii] * (double)(wi * wj * wk);
+                    }
+                }
+            }
+        }
+        S_c[(size_t)r * GMG_STRIDE + W.base + q] = (float)(0.125 * acc);
+    }
+}
+
 // lower blocks of the symmetric A_c: entry (row (m; J), column (mp; J + e)) with mp < m is entry
 // (row (mp; J + e), column (m; J)) of an upper block; the windows of (m, mp) and (mp, m) are mirror images.
 // One thread per (row, slot of a lower block).

@@ -478,12 +478,12 @@ static void gmg_build(Sim &s, GMG &M) {
         int GB = cdiv(3LL * L.nrows, GMG_BUILD_WARPS);
         const int *rng = shard ? L.rng : L.rng + 2;
         if (l == 1) {
-            auto kb = &k_gmg_build<true>;
+            auto kb = s.mg_build ? &k_gmg_build_g<true> : &k_gmg_build<true>;
             FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, rng, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)s.vcoef, (const int *)nullptr,
                         (const float *)s.vvol, 0);
         } else {
-            auto kb = &k_gmg_build<false>;
+            auto kb = s.mg_build ? &k_gmg_build_g<false> : &k_gmg_build<false>;
             FLIP_LAUNCH_SYNC(kb, GB, 32 * GMG_BUILD_WARPS, s.stream, L.g, F.g, (const int *)L.rows, rng, (const float *)L.diag, L.S,
                         (const float *)F.diag, (const float *)F.pn, (const float *)nullptr, (const int *)F.rowmap,
                         (const float *)F.S, F.nrows);
@@ -737,8 +737,8 @@ void stage_apply_viscosity(Sim &s, float dt) {
     s.visc_stats = SolveStats{0, 0, 0, 1, 0, 0, 0, 0};
     if (!s.viscosity_nonzero) return;  // src/fluidsimulation.cpp:171-184
     const Grid &g = s.g;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    cudaEvent_t e0, e1, es;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&es));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
     xch_update_cuts(s);   // k-slabs of this substep, balanced by liquid cells (no-op on one GPU)
     viscosity_volumes(s);
@@ -772,6 +772,7 @@ void stage_apply_viscosity(Sim &s, float dt) {
     if (s.visc_precond == 2) {
         GMG *M = gmg_get(s);
         gmg_build(s, *M);
+        CUDA_CHECK(cudaEventRecord(es, s.stream));
         P.z = s.cg_z;
         P.flexible = s.mg_flexible;
         h = run_cg_gmg(s, *M, P, diag, s.visc_tol, maxit, apply_on(P), s.visc_warm_start ? (const float *)s.vel : nullptr);
@@ -800,7 +801,9 @@ void stage_apply_viscosity(Sim &s, float dt) {
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
     CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1));
+    s.visc_setup_ms = 0;
+    if (s.visc_precond == 2) CUDA_CHECK(cudaEventElapsedTime(&s.visc_setup_ms, e0, es));
+    CUDA_CHECK(cudaEventDestroy(e0)); CUDA_CHECK(cudaEventDestroy(e1)); CUDA_CHECK(cudaEventDestroy(es));
     s.visc_stats.iters = h.iter; s.visc_stats.converged = h.converged; s.visc_stats.resid = h.resid;
     s.visc_stats.bmax = h.bmax; s.visc_stats.skipped = accept ? 0 : 2; s.visc_stats.blocks = s.count_host[0]; s.visc_stats.unknowns = s.count_host[1];
     s.visc_stats.ms = ms;

@@ -75,6 +75,8 @@ typedef struct flip_stats {
     float viscosity_solve_ms;
     int64_t pressure_unknowns;   /* rows of the last pressure system */
     int64_t viscosity_unknowns;  /* rows (U+V+W faces) of the last viscosity system */
+    float viscosity_setup_ms;    /* part of viscosity_solve_ms spent before the first CG iteration (volumes, rows, multigrid set-up) */
+    float reserved2;
 } flip_stats;
 
 /* ---- lifetime: FluidSimulation::initialize (src/fluidsimulation.cpp:26-43).  The domain-box
