@@ -83,6 +83,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s, s.cuts, 1);
     dev_alloc(s, s.plane_count, (size_t)nk + 2);
     dev_alloc(s, s.cgst, 2);
+    dev_alloc(s, s.grid_bar, 1);
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
     CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
@@ -657,6 +658,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_build") s.mg_build = (int)value;
+    else if (n == "pressure_resident") s.pres_resident = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;
     else if (n == "mg_sweeps_l1") s.mg_sweeps_l1 = (int)value;

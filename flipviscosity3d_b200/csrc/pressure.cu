@@ -12,6 +12,7 @@
 // on the active 8x8x8 blocks, and the preconditioner is the diagonal (see cg.h).
 #include "cg.h"
 #include "levelset_math.h"
+#include "resident.h"
 
 // rhs (into r) and stencil coefficients for every cell; non-unknown cells get zeros.
 __global__ void __launch_bounds__(CG_THREADS) k_pressure_build(Grid g, const int *__restrict__ glist, const int *__restrict__ gcount,
@@ -108,6 +109,47 @@ __global__ void __launch_bounds__(CG_THREADS) k_pressure_store(Grid g, const int
     }
 }
 
+// The whole CG in one persistent launch (resident.h).  Returns false when the system does not fit on chip (or the handle
+// is sharded): the caller then runs the launch-per-phase path.
+template <int CPT>
+static void launch_pcg_resident(Sim &s, PcgResParams &P, int G) {
+    auto k = &k_pcg_resident<CPT>;
+#ifdef FLIP_CPU_EMU
+    FLIP_LAUNCH_SYNC(k, 1, PCGR_THREADS, s.stream, P);
+#else
+    const size_t smem = (size_t)8 * CPT * PCGR_THREADS * sizeof(float);
+    CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {(void *)&P};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)k, dim3(G), dim3(PCGR_THREADS), args, smem, s.stream));
+#endif
+}
+static bool solve_pressure_resident(Sim &s, int pmaxit, CGState &h) {
+    if (!s.pres_resident || xch_of(s).nranks != 1) return false;
+    CUDA_CHECK(cudaMemcpyAsync(s.count_host, s.cell_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    const int nc = s.count_host[0];
+#ifdef FLIP_CPU_EMU
+    const int G = 1;
+#else
+    const int G = s.num_sms;
+#endif
+    const int need = cdiv(cdiv(nc, G), PCGR_THREADS);
+    if (need > PCGR_CPT_MAX) return false;
+    PcgResParams P;
+    P.g = s.g; P.cell_list = s.cell_list; P.cell_count = s.cell_count; P.coef = s.pcoef; P.b = s.cg_r; P.p = s.cg_s; P.x = s.cg_x;
+    P.part = s.part; P.bar = s.grid_bar; P.st = s.cgst; P.tol_abs = s.pressure_tol; P.maxit = pmaxit; P.strict = 1;
+    if (need <= 2) launch_pcg_resident<2>(s, P, G);
+    else if (need <= 4) launch_pcg_resident<4>(s, P, G);
+    else if (need <= 8) launch_pcg_resident<8>(s, P, G);
+    else launch_pcg_resident<PCGR_CPT_MAX>(s, P, G);
+    s.kernel_launches++;
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(s.cgst_host, s.cgst, sizeof(CGState), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    h = *s.cgst_host;
+    return true;
+}
+
 void solve_pressure(Sim &s, float dt) {
     const Grid &g = s.g;
     // small systems are not worth their hand-shakes: every rank solves the whole system (sim.h shard_min_unknowns)
@@ -140,7 +182,9 @@ void solve_pressure(Sim &s, float dt) {
             s.kernel_launches++;
         };
     };
-    if (s.cg_variant_pressure == 1) {
+    if (solve_pressure_resident(s, pmaxit, h)) {
+        // done: the whole solve ran in one persistent launch
+    } else if (s.cg_variant_pressure == 1) {
         // the search direction of the stencil kernel is u = M^-1 r here: it needs the zero halo too
         CUDA_CHECK(cudaMemsetAsync(s.cg_z, 0, sizeof(double) * (size_t)g.total, s.stream));
         CGParams Pu = P;

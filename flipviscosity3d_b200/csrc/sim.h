@@ -26,6 +26,8 @@ struct SolveStats {
 
 #define FLIP_CG_MAXGRID 1024  // upper bound on the persistent CG grid (partials per reduction)
 
+struct GridBar { unsigned count, gen; };   // grid-wide barrier of the persistent kernels (resident.h)
+
 struct Sim {
     Grid g;
     cudaStream_t stream = 0;
@@ -71,6 +73,7 @@ struct Sim {
     // Chronopoulos-Gear recurrences (2 kernels).  Measured on B200 at 256^3: the fused update kernel wins
     // for the scalar pressure system (9.3 vs 10.5 ms) and loses for the 3-component viscosity system
     // (86 vs 70 us/iteration: 18 fp64 values in flight per thread cost occupancy).
+    int pres_resident = 1;              // pressure CG as ONE persistent launch with its state on chip when it fits (resident.h)
     int cg_variant_pressure = 1;
     int cg_variant_viscosity = 0;
     int cg_grid_mult = 2;               // persistent CG grid = SMs x this (CTAs of 512 threads)                  // CG iterations launched between host convergence polls
@@ -131,6 +134,7 @@ struct Sim {
     int *cell_list = 0;       // [total] compact list of cells with >= 1 unknown (this solve)
     int *cell_count = 0;      // [1]
     double *part = 0;         // [6 * FLIP_MAX_RANKS * FLIP_CG_MAXGRID] reduction partials (kind-major, cg.h)
+    GridBar *grid_bar = 0;      // barrier state of the persistent kernels (resident.h)
     CGState *cgst = 0;        // [2] ping-pong
     CGState *cgst_host = 0;   // pinned
     int *count_host = 0;      // pinned [2]: active blocks, unknowns
