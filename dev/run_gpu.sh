@@ -1,8 +1,5 @@
-set -x
 cd $GRAFT_REPO_ROOT
-python dev/gmg_build_ab.py cuda 64 > gpurun_out/r2h_build_ab.log 2>&1; echo ab rc=$?
-python bench.py --steps 10 --warmup 3 --no-strict --no-cpu-baseline --param mg_build=0 > gpurun_out/r2h_bench_build0.json 2> gpurun_out/r2h_bench_build0.err; echo b0 rc=$?
-python bench.py --steps 10 --warmup 3 --no-strict --no-cpu-baseline > gpurun_out/r2h_bench_build1.json 2> gpurun_out/r2h_bench_build1.err; echo b1 rc=$?
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2h_launches.csv python tests/gpu_dev_gmg.py 256 2 2 > gpurun_out/r2h_ncu.log 2>&1; echo ncu rc=$?
-python tests/gpu_dev_launchlist.py gpurun_out/r2h_launches.csv 70 > gpurun_out/r2h_launches.txt; rm -f gpurun_out/r2h_launches.csv
-tail -3 gpurun_out/r2h_build_ab.log
+timeout 200 python tests/gpu_dev_gmg.py 256 2 4 pressure_resident=0 > gpurun_out/r2i_pres0.log 2>&1; echo p0 rc=$?
+timeout 200 python tests/gpu_dev_gmg.py 256 2 4 pressure_resident=1 > gpurun_out/r2i_pres1.log 2>&1; echo p1 rc=$?
+timeout 300 python -m pytest tests/test_stage_parity.py tests/test_edge_cases.py tests/test_configs_gpu.py -x -q -m gpu > gpurun_out/r2i_tests.log 2>&1; echo tests rc=$?
+tail -5 gpurun_out/r2i_pres0.log gpurun_out/r2i_pres1.log; tail -3 gpurun_out/r2i_tests.log

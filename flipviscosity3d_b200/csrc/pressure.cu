@@ -137,10 +137,12 @@ static bool solve_pressure_resident(Sim &s, int pmaxit, CGState &h) {
     if (need > PCGR_CPT_MAX) return false;
     PcgResParams P;
     P.g = s.g; P.cell_list = s.cell_list; P.cell_count = s.cell_count; P.coef = s.pcoef; P.b = s.cg_r; P.p = s.cg_s; P.x = s.cg_x;
-    P.part = s.part; P.bar = s.grid_bar; P.st = s.cgst; P.tol_abs = s.pressure_tol; P.maxit = pmaxit; P.strict = 1;
+    P.grid.slots = s.grid_slots; P.grid.bar = s.grid_bar; P.grid.gen = 0; P.st = s.cgst; P.tol_abs = s.pressure_tol; P.maxit = pmaxit; P.strict = 1;
     if (need <= 2) launch_pcg_resident<2>(s, P, G);
     else if (need <= 4) launch_pcg_resident<4>(s, P, G);
+    else if (need <= 6) launch_pcg_resident<6>(s, P, G);
     else if (need <= 8) launch_pcg_resident<8>(s, P, G);
+    else if (need <= 10) launch_pcg_resident<10>(s, P, G);
     else launch_pcg_resident<PCGR_CPT_MAX>(s, P, G);
     s.kernel_launches++;
     KERNEL_CHECK();

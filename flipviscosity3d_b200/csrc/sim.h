@@ -26,7 +26,7 @@ struct SolveStats {
 
 #define FLIP_CG_MAXGRID 1024  // upper bound on the persistent CG grid (partials per reduction)
 
-struct GridBar { unsigned count, gen; };   // grid-wide barrier of the persistent kernels (resident.h)
+struct GridBar { unsigned gen; int broken; };   // grid-wide exchange state of the persistent kernels (resident.h)
 
 struct Sim {
     Grid g;
@@ -63,6 +63,7 @@ struct Sim {
     // else costs no iterations (scipy prototype: 32 vs 31 at 128^3) and halves the level-1 traffic.
     int mg_sweeps_l0 = 3, mg_sweeps_l1 = 1;
     int mg_tma = 1;                     // explicit-level sweeps stage their coefficient rows with TMA bulk copies (gmg.h)
+    int mg_tail = 1;                    // levels >= 2 of the V-cycle as one persistent launch (gmg.h k_gmg_tail)
     int mg_build = 1;                   // Galerkin products: 1 = gather form (gmg.h k_gmg_build_g), 0 = lane-ordered scatter (bit-identical, slower)
     int mg_dense = 1;                   // exact dense solve on the first level with <= mg_dense_rows rows (else Jacobi sweeps there)
     int mg_dense_rows = 128;            // single-CTA Gauss-Jordan: 0.3 ms at 128 rows, 7 ms at 304 (measured) - keep it small
@@ -134,7 +135,7 @@ struct Sim {
     int *cell_list = 0;       // [total] compact list of cells with >= 1 unknown (this solve)
     int *cell_count = 0;      // [1]
     double *part = 0;         // [6 * FLIP_MAX_RANKS * FLIP_CG_MAXGRID] reduction partials (kind-major, cg.h)
-    GridBar *grid_bar = 0;      // barrier state of the persistent kernels (resident.h)
+    GridBar *grid_bar = 0; unsigned long long *grid_slots = 0;      // barrier state of the persistent kernels (resident.h)
     CGState *cgst = 0;        // [2] ping-pong
     CGState *cgst_host = 0;   // pinned
     int *count_host = 0;      // pinned [2]: active blocks, unknowns
