@@ -84,7 +84,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     dev_alloc(s, s.plane_count, (size_t)nk + 2);
     dev_alloc(s, s.cgst, 2);
     dev_alloc(s, s.grid_bar, 1);
-    dev_alloc(s, s.grid_slots, (size_t)2 * 1024 * 4);   // resident.h: [2][GRID_MAX_CTAS][GRID_SLOT_WORDS]
+    dev_alloc(s, s.grid_slots, (size_t)2 * (1024 + 1) * 4);   // resident.h: [2][GRID_MAX_CTAS + 1][GRID_SLOT_WORDS]
     CUDA_CHECK(cudaMallocHost((void **)&s.cgst_host, sizeof(CGState)));
     CUDA_CHECK(cudaMallocHost((void **)&s.count_host, 2 * sizeof(int)));
     CUDA_CHECK(cudaMallocHost((void **)&s.maxvel_host, sizeof(float)));
@@ -659,7 +659,6 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_build") s.mg_build = (int)value;
-    else if (n == "mg_tail") s.mg_tail = (int)value;
     else if (n == "pressure_resident") s.pres_resident = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;

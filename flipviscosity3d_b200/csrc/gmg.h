@@ -610,25 +610,27 @@ FLIP_HD int gmg_slot_offset(const Grid &g, int m, int slot) {
 
 // one warp: row r of an explicit level.  MODE 1: out = xi + w (b - A xi)   2: out = (b - A xi) / pn.
 // offs: the level's slot -> element offset table [3][GMG_STRIDE] (shared or global memory)
-template <int MODE>
+// L2: the vectors are read with L2-only loads (persistent kernels: other CTAs wrote them earlier in the same launch, and
+// loads through const __restrict__ pointers may take the non-coherent path, which a fence does not invalidate)
+template <int MODE, bool L2 = false>
 FLIP_D void gmg_row_apply(const Grid &g, const int *__restrict__ rows, const float *__restrict__ S, const float *__restrict__ wj,
-                          const float *__restrict__ b, const float *__restrict__ xi, float *__restrict__ out,
-                          const float *__restrict__ pn, const int *offs, int r, int lane) {
+                          const float *b, const float *xi, float *out, const float *__restrict__ pn, const int *offs, int r, int lane) {
     const int enc = rows[r];
     const int m = enc / g.total, id = enc - m * g.total;
     const float *__restrict__ Sr = S + (size_t)r * GMG_STRIDE;
-    const float *__restrict__ xc = xi + id;
+    const float *xc = xi + id;
     const int *om = offs + m * GMG_STRIDE;
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         int slot = lane + 32 * t;
-        if (slot < GMG_STRIDE) acc += Sr[slot] * xc[om[slot]];
+        if (slot < GMG_STRIDE) acc += Sr[slot] * (L2 ? ld_cg(xc + om[slot]) : xc[om[slot]]);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
-        if (MODE == 1) out[enc] = xi[enc] + wj[r] * (b[enc] - acc);
-        else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
+        const float bv = L2 ? ld_cg(b + enc) : b[enc];
+        if (MODE == 1) out[enc] = (L2 ? ld_cg(xi + enc) : xi[enc]) + wj[r] * (bv - acc);
+        else { float p = pn[enc]; out[enc] = p > 0.0f ? (bv - acc) / p : 0.0f; }
     }
 }
 
@@ -825,7 +827,8 @@ __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__
 }
 
 // value of the coarse correction P x_c at fine face (m; i,j,k), not yet divided by pn
-FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float *__restrict__ xc) {
+template <bool L2 = false>
+FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float *xc) {
     int pi[2], pj[2], pk[2];
     float wi[2], wj[2], wk[2];
     gmg_parents(m == 0, i, pi[0], pi[1], wi[0], wi[1]);
@@ -840,7 +843,7 @@ FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float 
                 if (w == 0.0f) continue;
                 int I = pi[a], J = pj[b2], K = pk[c2];
                 if (I < 0 || J < 0 || K < 0 || I > gc.ni || J > gc.nj || K > gc.nk) continue;
-                v += w * x[gidx(gc, I, J, K)];   // x_c is exactly 0 where the coarse face is not an unknown
+                v += w * (L2 ? ld_cg(x + gidx(gc, I, J, K)) : x[gidx(gc, I, J, K)]);   // x_c is exactly 0 where the coarse face is not an unknown
             }
     return v;
 }
@@ -884,8 +887,9 @@ __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *_
 // coarse b = P^T r / 8 (r already divided by pn) and the first sweep from zero, x0 = w b.  One warp per coarse
 // row: the <= 48 fine children are spread over the lanes (two per lane), so a row costs one memory round trip
 // instead of 48 serialised ones.
+template <bool L2 = false>
 FLIP_D void gmg_row_restrict(const Grid &gc, const int *__restrict__ rows, const float *__restrict__ wjc, const Grid &gf,
-                             const float *__restrict__ rf, float *__restrict__ bc, float *__restrict__ x0, int r, int lane) {
+                             const float *rf, float *bc, float *x0, int r, int lane) {
     const int enc = rows[r];
     const int m = enc / gc.total, id = enc - m * gc.total;
     int I, J, K;
@@ -902,7 +906,8 @@ FLIP_D void gmg_row_restrict(const Grid &gc, const int *__restrict__ rows, const
         float wj = m == 1 ? (b2 == 1 ? 1.0f : (b2 < 3 ? 0.5f : 0.0f)) : ((b2 == 1 || b2 == 2) ? 0.75f : 0.25f);
         float wk = m == 2 ? (c2 == 1 ? 1.0f : (c2 < 3 ? 0.5f : 0.0f)) : ((c2 == 1 || c2 == 2) ? 0.75f : 0.25f);
         float w = wi * wj * wk;
-        if (w != 0.0f && fi >= 0 && fj >= 0 && fk >= 0 && fi <= gf.ni && fj <= gf.nj && fk <= gf.nk) acc += w * rr[gidx(gf, fi, fj, fk)];
+        if (w != 0.0f && fi >= 0 && fj >= 0 && fk >= 0 && fi <= gf.ni && fj <= gf.nj && fk <= gf.nk)
+            acc += w * (L2 ? ld_cg(rr + gidx(gf, fi, fj, fk)) : rr[gidx(gf, fi, fj, fk)]);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -989,98 +994,3 @@ __global__ void __launch_bounds__(256) k_gmg_dense_apply(GLevelDev L, const floa
     }
 }
 
-// ---- the coarse tail of the V-cycle as ONE persistent launch ---------------------------------------------------------
-// Levels >= l0 (level 2 on one GPU: 39 k rows and fewer at 256^3) are latency bound: ~26 launches of 4-12 us per V-cycle
-// for a few microseconds of work each.  k_gmg_tail runs the whole down- and upstroke of those levels - restriction into
-// level l0, sweeps, residuals, the dense coarsest solve, prolongations, post-sweeps - with one CTA per SM and a grid-wide
-// flag exchange (resident.h) where the launch boundaries were.  Same row functions, same order of operations as the
-// launch-per-phase cycle: bit-identical results.
-struct GTailLv {
-    Grid g;
-    const int *rows, *nrows, *offs;
-    const float *S, *wj, *pn;
-    float *x[2], *b, *r;
-    int pre;
-};
-struct GTailParams {
-    int l0, last, dense_last, coarse_sweeps;
-    GTailLv lv[GMG_MAX_LEVELS];   // entries l0 - 1 (grid and r only) .. last
-    const float *Ainv;
-    GridCtx grid;
-    const CGState *st;
-};
-#define GMG_TAIL_THREADS 1024
-
-// the buffer (0/1) that holds level l's iterate after the tail (or the whole cycle's work on that level) is done
-static inline int gmg_tail_final_cur(int l, int last, bool dense_last, int coarse_sweeps, const int *pre) {
-    int cur = 0;
-    if (l == last) { if (!dense_last) cur = coarse_sweeps & 1; return cur; }
-    cur = (pre[l] - 1) & 1;          // downstroke: pre - 1 sweeps after the fused first one
-    cur ^= pre[l] & 1;               // upstroke: pre sweeps
-    return cur;
-}
-
-__global__ void __launch_bounds__(GMG_TAIL_THREADS, 1) k_gmg_tail(GTailParams T) {
-    __shared__ double sm[CG_THREADS / 32];
-    if (T.st && T.st->done) return;
-    GridCtx gc = T.grid;
-    grid_begin(gc);
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-    int cur[GMG_MAX_LEVELS];
-    bool ok = true;
-#define GMG_TAIL_SYNC() { double n0 = 0.0, n1 = 0.0; ok = grid_allreduce2<false, false, true>(gc, n0, n1, sm) && ok; if (!ok) return; }
-    for (int l = T.l0; l <= T.last; l++) {
-        const GTailLv &L = T.lv[l];
-        const GTailLv &F = T.lv[l - 1];
-        const int n = *L.nrows;
-        for (int r = gw; r < n; r += nw) gmg_row_restrict(L.g, L.rows, L.wj, F.g, F.r, L.b, L.x[0], r, lane);
-        cur[l] = 0;
-        GMG_TAIL_SYNC();
-        if (l == T.last && T.dense_last) {
-            for (int i = gw; i < n; i += nw) {
-                float acc = 0.0f;
-                for (int j = lane; j < n; j += 32) acc += T.Ainv[i * n + j] * ld_cg(L.b + L.rows[j]);
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) L.x[0][L.rows[i]] = acc;
-            }
-            GMG_TAIL_SYNC();
-            continue;
-        }
-        const int sweeps = l == T.last ? 1 + T.coarse_sweeps : L.pre;
-        for (int k = 1; k < sweeps; k++) {
-            for (int r = gw; r < n; r += nw) gmg_row_apply<1>(L.g, L.rows, L.S, L.wj, L.b, L.x[cur[l]], L.x[cur[l] ^ 1], L.pn, L.offs, r, lane);
-            cur[l] ^= 1;
-            GMG_TAIL_SYNC();
-        }
-        if (l < T.last) {
-            for (int r = gw; r < n; r += nw) gmg_row_apply<2>(L.g, L.rows, L.S, L.wj, L.b, L.x[cur[l]], L.r, L.pn, L.offs, r, lane);
-            GMG_TAIL_SYNC();
-        }
-    }
-    for (int l = T.last - 1; l >= T.l0; l--) {
-        const GTailLv &L = T.lv[l];
-        const GTailLv &C = T.lv[l + 1];
-        const int n = *L.nrows;
-        const float *xc = C.x[cur[l + 1]];
-        float *xf = L.x[cur[l]];
-        for (int r = gt; r < n; r += nt) {
-            const int enc = L.rows[r];
-            const int m = enc / L.g.total, id = enc - m * L.g.total;
-            const float p = L.pn[enc];
-            if (p <= 0.0f) continue;
-            int i, j, k;
-            gmg_unflatten(L.g, id, i, j, k);
-            xf[enc] += gmg_interp(m, i, j, k, C.g, xc) / p;
-        }
-        GMG_TAIL_SYNC();
-        for (int k = 0; k < L.pre; k++) {
-            for (int r = gw; r < n; r += nw) gmg_row_apply<1>(L.g, L.rows, L.S, L.wj, L.b, L.x[cur[l]], L.x[cur[l] ^ 1], L.pn, L.offs, r, lane);
-            cur[l] ^= 1;
-            if (k + 1 < L.pre || l > T.l0) GMG_TAIL_SYNC();   // nothing follows the last sweep on level l0
-        }
-    }
-#undef GMG_TAIL_SYNC
-    grid_end(gc);
-}

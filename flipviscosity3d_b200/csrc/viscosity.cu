@@ -557,12 +557,8 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
     FLIP_LAUNCH_X(sh, l0_resid, G0, 256, s.stream, P0, r_in, (const float *)L0.x[cur[0]], L0.r, (double *)nullptr, w, st);
     if (sh) xch_push_halo(s, L0.g, L0.r, sizeof(float), 3, 0, 2);
     s.kernel_launches += M.pre_l[0] + 1;
-    // Levels >= l0 run as one persistent launch (gmg.h k_gmg_tail): level 2 on one GPU; level 3 on a sharded handle,
-    // where the restriction into level 2 is still cut by rows and gathered.
-    int l0 = last + 1;
-    if (s.mg_tail) { l0 = sh ? GMG_SHARD_SWEEP_LEVELS + 2 : 2; if (l0 > last) l0 = last + 1; }
     // explicit levels, downstroke
-    for (int l = 1; l <= last && l < l0; l++) {
+    for (int l = 1; l <= last; l++) {
         GLevel &L = M.lv[l];
         // sweeps on this rank's rows only (never the dense last level: its solve needs the whole right-hand side)
         const bool own = sh && l <= GMG_SHARD_SWEEP_LEVELS && !(l == last && M.dense_last);
@@ -596,26 +592,8 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         }
         s.kernel_launches += sweeps + (l < last ? 1 : 0);
     }
-    if (l0 <= last) {
-        GTailParams T;
-        T.l0 = l0; T.last = last; T.dense_last = M.dense_last ? 1 : 0; T.coarse_sweeps = M.coarse_sweeps;
-        for (int l = l0 - 1; l <= last; l++) {
-            GLevel &L = M.lv[l];
-            GTailLv &t = T.lv[l];
-            t.g = L.g; t.rows = L.rows; t.nrows = L.nrows_dev; t.offs = L.offs; t.S = L.S; t.wj = L.wj; t.pn = L.pn;
-            t.x[0] = L.x[0]; t.x[1] = L.x[1]; t.b = L.b; t.r = L.r; t.pre = M.pre_l[l];
-        }
-        T.Ainv = M.Ainv; T.grid.slots = s.grid_slots; T.grid.bar = s.grid_bar; T.grid.gen = 0; T.st = st;
-#ifdef FLIP_CPU_EMU
-        FLIP_LAUNCH_SYNC(k_gmg_tail, 1, 256, s.stream, T);
-#else
-        FLIP_LAUNCH_SYNC(k_gmg_tail, s.num_sms, GMG_TAIL_THREADS, s.stream, T);   // one CTA per SM: all co-resident
-#endif
-        cur[l0] = gmg_tail_final_cur(l0, last, M.dense_last, M.coarse_sweeps, M.pre_l);
-        s.kernel_launches++;
-    }
     // upstroke
-    for (int l = (l0 <= last ? l0 : last) - 1; l >= 1; l--) {
+    for (int l = last - 1; l >= 1; l--) {
         GLevel &L = M.lv[l];
         const bool own = sh && l <= GMG_SHARD_SWEEP_LEVELS;   // l < last here: never the dense level
         GLevelDev D = gmg_dev(s, L, own);
@@ -698,7 +676,7 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
         mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
-        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma); mix((unsigned long long)s.mg_tail);
+        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
             mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
