@@ -659,6 +659,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_tma") s.mg_tma = (int)value;
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_build") s.mg_build = (int)value;
+    else if (n == "mg_xgroup") s.mg_xgroup = (int)value;
     else if (n == "pressure_resident") s.pres_resident = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;

@@ -30,6 +30,7 @@
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
+#define GMG_XLINES 72      // x-lines of a row's window: 65 for U rows, 51 for V and W rows
 
 // one axis of the prolongation: fine index n -> up to two coarse indices and weights
 FLIP_D void gmg_parents(bool own, int n, int &p0, int &p1, float &w0, float &w1) {
@@ -103,6 +104,12 @@ struct GLevel {
     float *S = 0;         // [nrows * GMG_STRIDE]
     float *wj = 0;        // [nrows] smoothing weight per row
     int *offs = 0;        // [3 * GMG_STRIDE] slot -> element offset table (set once: it only depends on the grid)
+    // x-groups (first explicit level only): the rows of one 8-wide x-run of a tile (same component, j, k) are consecutive
+    // in `rows`; a group = {first row, 8-bit mask of the cells of the run that are unknowns}.  k_gmg_sweep_x / _restrict_x
+    int2 *groups = 0;     // [<= 3T/8]
+    int *gtile_off = 0;   // [ntiles + 1] first group of every (plane, tile)
+    int *grng = 0;        // device [4]: {first, end} group of this rank's slab, then {0, ngroups}
+    int4 *lines = 0;      // [3 * GMG_XLINES] x-lines of a row's window (set once), gmg_make_lines
     bool owns = false;
 };
 
@@ -131,6 +138,9 @@ struct GLevelDev {
     const float *S;
     const float *wj;     // [nrows] smoothing weights
     const int *offs;     // [3 * GMG_STRIDE] element offset of every slot, per row component (0 for padding)
+    const int2 *groups;  // x-groups of the level (null: none built)
+    const int *grng;     // {first, end} group this launch works on
+    const int4 *lines;
 };
 
 FLIP_D void gmg_unflatten(const Grid &g, int id, int &i, int &j, int &k) {
@@ -163,34 +173,42 @@ __global__ void __launch_bounds__(256) k_gmg_flags(Grid gc, Grid gf, const float
 // tile = one k-plane of an 8x8x8 block (64 cells, two warps); tile id = plane * (nby * nbx) + bj * nbx + bi.
 // per_tile[tile] = unknowns in the tile (all three components); zero for tiles of inactive blocks (memset by the host).
 __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_counts(Grid g, const int *__restrict__ list, const int *__restrict__ count,
-                                                                const float *__restrict__ diag, int *__restrict__ per_tile) {
+                                                                const float *__restrict__ diag, int *__restrict__ per_tile,
+                                                                int *__restrict__ per_tile_g /* x-groups per tile, or null */) {
     __shared__ int wsum[CG_THREADS / 32];
+    __shared__ int gsum[CG_THREADS / 32];
     int nb = *count;
     size_t T = (size_t)g.total;
     const int tpp = g.nbx * g.nby;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const int blk = list[b];
         BlockCell c = block_cell(g, blk, threadIdx.x);
-        int n = 0;
-        if (c.inside) {
-            int id = gidx(g, c.i, c.j, c.k);
-            for (int m = 0; m < 3; m++) n += diag[m * T + id] != 0.0f ? 1 : 0;
+        int n = 0, ng = 0;
+        const int id = c.inside ? gidx(g, c.i, c.j, c.k) : 0;
+        for (int m = 0; m < 3; m++) {
+            const bool has = c.inside && diag[m * T + id] != 0.0f;
+            n += has ? 1 : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, has);   // a warp = 4 x-runs of 8 cells
+            for (int yy = 0; yy < 4; yy++) ng += ((bal >> (8 * yy)) & 0xffu) != 0u ? 1 : 0;
         }
         for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
+        if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = n; gsum[threadIdx.x >> 5] = ng; }
         __syncthreads();
         if (threadIdx.x < 8) {   // thread p: plane p of the block = warps 2p, 2p+1
             int bk = blk / tpp, rest = blk - bk * tpp;
             per_tile[(bk * FLIP_B + threadIdx.x) * tpp + rest] = wsum[2 * threadIdx.x] + wsum[2 * threadIdx.x + 1];
+            if (per_tile_g) per_tile_g[(bk * FLIP_B + threadIdx.x) * tpp + rest] = gsum[2 * threadIdx.x] + gsum[2 * threadIdx.x + 1];
         }
     }
 }
 
 __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *__restrict__ list, const int *__restrict__ count,
                                                               const float *__restrict__ diag, const int *__restrict__ tile_off,
-                                                              int *__restrict__ rows, int *__restrict__ rowmap) {
+                                                              int *__restrict__ rows, int *__restrict__ rowmap,
+                                                              const int *__restrict__ gtile_off, int2 *__restrict__ groups /* or null */) {
     __shared__ int wsum[CG_THREADS / 32];
+    __shared__ int gsum[CG_THREADS / 32];
     int nb = *count;
     size_t T = (size_t)g.total;
     const int tpp = g.nbx * g.nby;
@@ -201,17 +219,32 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *
         int id = c.inside ? gidx(g, c.i, c.j, c.k) : 0;
         const int bk = blk / tpp, rest = blk - bk * tpp;
         int base = tile_off[(bk * FLIP_B + (wid >> 1)) * tpp + rest];   // first row of this thread's plane tile
+        int gbase = groups ? gtile_off[(bk * FLIP_B + (wid >> 1)) * tpp + rest] : 0;
         for (int m = 0; m < 3; m++) {
             bool has = c.inside && diag[m * T + id] != 0.0f;
             unsigned bal = __ballot_sync(0xffffffffu, has);
+            int ng = 0;
+            for (int yy = 0; yy < 4; yy++) ng += ((bal >> (8 * yy)) & 0xffu) != 0u ? 1 : 0;
             __syncthreads();
-            if (lane == 0) wsum[wid] = __popc(bal);
+            if (lane == 0) { wsum[wid] = __popc(bal); gsum[wid] = ng; }
             __syncthreads();
             const int before = (wid & 1) ? wsum[wid - 1] : 0, total = wsum[wid & ~1] + wsum[wid | 1];
+            const int r = base + before + __popc(bal & ((1u << lane) - 1u));
             if (has) {
-                int r = base + before + __popc(bal & ((1u << lane) - 1u));
                 rows[r] = (int)(m * T + id);
                 rowmap[m * T + id] = r;
+            }
+            if (groups) {
+                // the first unknown of every non-empty 8-cell x-run writes the run's group (tile order: component, warp, run)
+                const int yy = lane >> 3;
+                const unsigned run = (bal >> (8 * yy)) & 0xffu;
+                if (has && (run & ((1u << (lane & 7)) - 1u)) == 0u) {
+                    int gi = gbase + ((wid & 1) ? gsum[wid - 1] : 0);
+                    for (int y2 = 0; y2 < yy; y2++) gi += ((bal >> (8 * y2)) & 0xffu) != 0u ? 1 : 0;
+                    int2 G; G.x = r; G.y = (int)run;
+                    groups[gi] = G;
+                }
+                gbase += gsum[wid & ~1] + gsum[wid | 1];
             }
             base += total;
         }
@@ -221,17 +254,20 @@ __global__ void __launch_bounds__(CG_THREADS) k_gmg_row_fill(Grid g, const int *
 // row ranges of a level: rng[0..1] = this rank's slab of planes (cuts of `level`, or everything when cuts == null),
 // rng[2..3] = all rows
 __global__ void k_gmg_ranges(const int *__restrict__ tile_off, int ntiles, int tpp, const Cuts *__restrict__ cuts, int level, int rank,
-                             int *__restrict__ rng, int *__restrict__ nrows) {
+                             int *__restrict__ rng, int *__restrict__ nrows, const int *__restrict__ gtile_off, int *__restrict__ grng) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int n = tile_off[ntiles];
     int a = 0, b = n;
+    int t0 = 0, t1 = ntiles;
     if (cuts) {
-        int t0 = cuts->c[level][rank] * tpp, t1 = cuts->c[level][rank + 1] * tpp;
-        a = tile_off[t0 < ntiles ? t0 : ntiles];
-        b = tile_off[t1 < ntiles ? t1 : ntiles];
+        t0 = cuts->c[level][rank] * tpp; t1 = cuts->c[level][rank + 1] * tpp;
+        t0 = t0 < ntiles ? t0 : ntiles; t1 = t1 < ntiles ? t1 : ntiles;
+        a = tile_off[t0];
+        b = tile_off[t1];
     }
     rng[0] = a; rng[1] = b; rng[2] = 0; rng[3] = n;
     *nrows = n;
+    if (grng) { grng[0] = gtile_off[t0]; grng[1] = gtile_off[t1]; grng[2] = 0; grng[3] = gtile_off[ntiles]; }
 }
 
 // pn: prolongation normaliser of every unknown of the fine level
@@ -744,6 +780,189 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     xch_leave(L.X, false);
 }
 #endif
+
+// ---- x-group kernels of the first explicit level --------------------------------------------------------------------
+// The warp-per-row sweep is bound by L1 (ncu: l1tex 79 %, DRAM at half its peak): a row gathers 235 vector values, and
+// the 32 lanes of one load touch ~8 different 128-byte lines (slots run along x for only 3-5 values before they jump to
+// the next j or k).  Here a warp takes a GROUP of up to 8 rows that are neighbours along x (one 8-cell run of a tile,
+// same component, j, k - consecutive rows of the k-plane-major row list) and walks the window LINE by line (a line =
+// the 3-5 slots of one (column component, dj, dk)): lane (xr, d) = (row of the run, offset along x) reads
+// x[i0 + xr + lo + d], so the 32 lanes of a load cover ~12 consecutive floats - one cache line instead of eight.
+// 65 (U rows) or 51 (V, W rows) line loads per group against 8 x 8 row loads of ~8 lines each: ~7x fewer L1 wavefronts,
+// which leaves the coefficient stream as the only bound.  The group's coefficient rows (<= 8 x 960 B, contiguous in S)
+// are staged by TMA bulk copies into shared memory, two groups in flight per warp, one mbarrier per buffer, rows padded
+// to 976 B so that the (xr, d) read pattern is bank-conflict free.
+#define GMG_XWARPS 4
+#define GMG_XROWS 8
+#define GMG_XSTRIDE 244
+#define GMG_XSMEM (GMG_XWARPS * 2 * GMG_XROWS * GMG_XSTRIDE * 4)
+
+// lines of a row's window, per row component m: {element offset of the line's first slot relative to the row's own
+// cell (column component included), first slot, slots in the line, -}; entry [m][0].w = number of lines
+static inline void gmg_make_lines(const Grid &g, std::vector<int4> &out) {
+    int4 z; z.x = z.y = z.z = z.w = 0;
+    out.assign(3 * GMG_XLINES, z);
+    for (int m = 0; m < 3; m++) {
+        int n = 0;
+        for (int mp = 0; mp < 3; mp++) {
+            GWin W = gmg_window(m, mp);
+            for (int dk = 0; dk < W.n[2]; dk++)
+                for (int dj = 0; dj < W.n[1]; dj++) {
+                    int4 e;
+                    e.x = mp * g.total + W.lo[0] + (W.lo[1] + dj) * SY(g) + (W.lo[2] + dk) * SZ(g);
+                    e.y = W.base + (dk * W.n[1] + dj) * W.n[0];
+                    e.z = W.n[0];
+                    e.w = 0;
+                    out[m * GMG_XLINES + n++] = e;
+                }
+        }
+        out[m * GMG_XLINES].w = n;
+    }
+}
+
+#ifdef FLIP_CPU_EMU
+FLIP_D void gmg_x_init(unsigned long long *, int) {}
+FLIP_D void gmg_x_stage(float *dst, const float *S, int r0, int cnt, unsigned long long *, int lane) {
+    for (int row = 0; row < cnt; row++)
+        for (int q = lane; q < GMG_STRIDE; q += 32) dst[row * GMG_XSTRIDE + q] = S[(size_t)(r0 + row) * GMG_STRIDE + q];
+    __syncwarp();
+}
+FLIP_D void gmg_x_wait(unsigned long long *, unsigned) { __syncwarp(); }
+#else
+FLIP_D void gmg_x_init(unsigned long long *bar, int lane) {
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(bar + 1)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+}
+// lane 0 announces the bytes, lanes < cnt issue one 960-byte bulk copy each (global -> shared, completion on the mbarrier)
+FLIP_D void gmg_x_stage(float *dst, const float *S, int r0, int cnt, unsigned long long *bar, int lane) {
+    if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gmg_smem(bar)), "r"((unsigned)(cnt * GMG_STRIDE * 4)) : "memory");
+    __syncwarp();
+    if (lane < cnt)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gmg_smem(dst + lane * GMG_XSTRIDE)),
+                     "l"(S + (size_t)(r0 + lane) * GMG_STRIDE), "r"((unsigned)(GMG_STRIDE * 4)), "r"(gmg_smem(bar))
+                     : "memory");
+}
+FLIP_D void gmg_x_wait(unsigned long long *bar, unsigned parity) { gmg_bar_wait(bar, parity); }
+#endif
+
+// MODE 1: out = xi + w (b - A xi)   2: out = (b - A xi) / pn.  One warp per x-group; grid-stride over the group range.
+template <int MODE>
+__global__ void __launch_bounds__(32 * GMG_XWARPS) k_gmg_sweep_x(GLevelDev L, const float *__restrict__ b, const float *__restrict__ xi,
+                                                                  float *__restrict__ out, const float *__restrict__ pn,
+                                                                  const CGState *__restrict__ st) {
+#ifdef FLIP_CPU_EMU
+    __shared__ float Sst[GMG_XWARPS * 2 * GMG_XROWS * GMG_XSTRIDE];
+#else
+    extern __shared__ __align__(128) float Sst[];
+#endif
+    __shared__ int4 lines[3 * GMG_XLINES];
+    __shared__ unsigned long long bars[GMG_XWARPS][2];
+    if (st && st->done) return;
+    if (!xch_enter(L.X, L.X.nbr != 0)) return;
+    for (int q = threadIdx.x; q < 3 * GMG_XLINES; q += blockDim.x) lines[q] = L.lines[q];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    gmg_x_init(bars[wid], lane);
+    __syncthreads();
+    float *sbuf[2] = {Sst + (wid * 2 + 0) * GMG_XROWS * GMG_XSTRIDE, Sst + (wid * 2 + 1) * GMG_XROWS * GMG_XSTRIDE};
+    const int g0 = L.grng[0], g1 = L.grng[1];
+    const int nw = gridDim.x * GMG_XWARPS;
+    const int T = L.g.total;
+    const int xr = lane & 7, d4 = lane >> 3;
+    unsigned phase[2] = {0u, 0u};
+    int buf = 0;
+    int g = g0 + blockIdx.x * GMG_XWARPS + wid;
+    if (g < g1) { const int2 G = L.groups[g]; gmg_x_stage(sbuf[0], L.S, G.x, __popc((unsigned)G.y), &bars[wid][0], lane); }
+    for (; g < g1; g += nw) {
+        const int gn = g + nw;
+        if (gn < g1) { const int2 Gn = L.groups[gn]; gmg_x_stage(sbuf[buf ^ 1], L.S, Gn.x, __popc((unsigned)Gn.y), &bars[wid][buf ^ 1], lane); }
+        const int2 G = L.groups[g];
+        const int r0 = G.x;
+        const unsigned mask = (unsigned)G.y;
+        const int enc0 = L.rows[r0];
+        const int m = enc0 / T;
+        const int encb = enc0 - (__ffs(mask) - 1);          // the run's first cell (row component included)
+        const bool has = (mask >> xr) & 1u;
+        const int rowl = __popc(mask & ((1u << xr) - 1u));
+        const float *__restrict__ xb = xi + (encb - m * T) + xr;
+        const int4 *ln = lines + m * GMG_XLINES;
+        const int nl = ln[0].w;
+        gmg_x_wait(&bars[wid][buf], phase[buf]);
+        phase[buf] ^= 1u;
+        const float *Sr = sbuf[buf] + rowl * GMG_XSTRIDE;
+        float acc = 0.0f;
+        if (has) {
+#pragma unroll 4
+            for (int l = 0; l < nl; l++) {
+                const int4 e = ln[l];
+                for (int d = d4; d < e.z; d += 4) acc += Sr[e.y + d] * xb[e.x + d];
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (has && d4 == 0) {
+            const int enc = encb + xr, r = r0 + rowl;
+            if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
+            else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
+        }
+        __syncwarp();   // every lane is done with this buffer before the copy after next overwrites it
+        buf ^= 1;
+    }
+    xch_leave(L.X, false);
+}
+
+// coarse b = P^T r / 8 and the first sweep from zero (k_gmg_restrict_first) over the x-groups of the coarse level: lane
+// (xr, a) reads fine x = 2 (i0 + xr) - 1 + a of every (fj, fk) line of the 4 x 4 children box, so a load covers 18
+// consecutive fine values instead of 8 scattered lines
+__global__ void __launch_bounds__(256) k_gmg_restrict_x(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
+                                                         float *__restrict__ x0, const CGState *__restrict__ st) {
+    if (st && st->done) return;
+    if (!xch_enter(C.X, C.X.nbr != 0)) return;
+    const int g0 = C.grng[0], g1 = C.grng[1];
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int T = C.g.total;
+    const int xr = lane & 7, a = lane >> 3;
+    for (int g = g0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < g1; g += nwarps) {
+        const int2 G = C.groups[g];
+        const int r0 = G.x;
+        const unsigned mask = (unsigned)G.y;
+        const int enc0 = C.rows[r0];
+        const int m = enc0 / T;
+        const int encb = enc0 - (__ffs(mask) - 1);
+        int I0, J, K;
+        gmg_unflatten(C.g, encb - m * T, I0, J, K);
+        const bool has = (mask >> xr) & 1u;
+        const int fi = 2 * (I0 + xr) - 1 + a;
+        const float wi = gmg_child_weight(m == 0, a);
+        const float *rr = rf + (size_t)m * gf.total;
+        const bool xin = has && wi != 0.0f && fi >= 0 && fi <= gf.ni;
+        float acc = 0.0f;
+        for (int c2 = 0; c2 < 4; c2++) {
+            const int fk = 2 * K - 1 + c2;
+            const float wk = gmg_child_weight(m == 2, c2);
+            if (wk == 0.0f || fk < 0 || fk > gf.nk) continue;
+            for (int b2 = 0; b2 < 4; b2++) {
+                const int fj = 2 * J - 1 + b2;
+                const float wj = gmg_child_weight(m == 1, b2);
+                if (wj == 0.0f || fj < 0 || fj > gf.nj) continue;
+                if (xin) acc += wi * wj * wk * rr[gidx(gf, fi, fj, fk)];
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (has && a == 0) {
+            const int enc = encb + xr, r = r0 + __popc(mask & ((1u << xr) - 1u));
+            const float bv = 0.125f * acc;
+            bc[enc] = bv;
+            x0[enc] = C.wj[r] * bv;
+        }
+    }
+    xch_leave(C.X, false);
+}
 
 // ---- level 0 on the solver's compact cell list ------------------------------------------------
 // Same loads as k_visc_apply (viscosity.cu), in fp32: one thread per cell index that holds an unknown,

@@ -347,6 +347,10 @@ static GMG *gmg_get(Sim &s) {
     CUDA_CHECK(cudaMallocHost((void **)&M->count_host, 4 * sizeof(int)));
     heap_alloc(s, M->dense, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
     heap_alloc(s, M->Ainv, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
+#ifndef FLIP_CPU_EMU
+    CUDA_CHECK(cudaFuncSetAttribute(k_gmg_sweep_x<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GMG_XSMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gmg_sweep_x<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GMG_XSMEM));
+#endif
     Grid g = s.g;
     for (int l = 0; l < GMG_MAX_LEVELS; l++) {
         GLevel &L = M->lv[l];
@@ -373,6 +377,15 @@ static GMG *gmg_get(Sim &s) {
             for (int m = 0; m < 3; m++)
                 for (int slot = 0; slot < GMG_SLOTS; slot++) offs[m * GMG_STRIDE + slot] = gmg_slot_offset(g, m, slot);
             CUDA_CHECK(cudaMemcpyAsync(L.offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+            std::vector<int4> lines;
+            if (l == 1) {   // x-groups: the first explicit level is the one whose sweeps matter (gmg.h k_gmg_sweep_x)
+                heap_alloc(s, L.groups, 3 * T / 8 + 8);
+                heap_alloc(s, L.gtile_off, (size_t)L.ntiles + 1);
+                heap_alloc(s, L.grng, 4);
+                heap_alloc(s, L.lines, 3 * GMG_XLINES);
+                gmg_make_lines(g, lines);
+                CUDA_CHECK(cudaMemcpyAsync(L.lines, lines.data(), lines.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
+            }
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
             L.owns = true;
         }
@@ -402,6 +415,8 @@ static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
     GLevelDev d;
     d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
     d.rng = own ? L.rng : L.rng + 2;
+    d.groups = L.groups; d.lines = L.lines;
+    d.grng = L.grng ? (own ? L.grng : L.grng + 2) : nullptr;
     d.X = xch_of(s);
     if (!own) d.X.nranks = 1;
     return d;
@@ -409,6 +424,11 @@ static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
 static int gmg_grid(const Sim &s, const GLevel &L) {
     int G = cg_grid(s);
     return L.g.nblocks < G ? L.g.nblocks : G;
+}
+static int gmg_group_grid(const Sim &s, const GLevel &L) {
+    // one warp per x-group (<= 8 rows), GMG_XWARPS warps per CTA, three 61 KB CTAs per SM; sized from the row capacity
+    long long G = cdiv((long long)L.cap / 4 + 1, GMG_XWARPS), cap = s.num_sms * 3;
+    return (int)(G < 1 ? 1 : (G > cap ? cap : G));
 }
 static int gmg_row_grid(const Sim &s, const GLevel &L) {
     // one warp per row, 8 warps per CTA.  Sized from the row CAPACITY (which only changes when the level is
@@ -454,13 +474,16 @@ static void gmg_build(Sim &s, GMG &M) {
         DiagViscosity d{L.diag, L.g.total};
         build_block_list_on<3>(s, L.g, d, L.blk_flag, L.blk_list, L.blk_count);
         int G = gmg_grid(s, L);
+        const bool xg = L.groups != nullptr;
+        if (xg) CUDA_CHECK(cudaMemsetAsync(L.gtile_off, 0, ((size_t)L.ntiles + 1) * sizeof(int), s.stream));
         FLIP_LAUNCH_SYNC(k_gmg_row_counts, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
-                         (const float *)L.diag, L.tile_off);
+                         (const float *)L.diag, L.tile_off, xg ? L.gtile_off : (int *)nullptr);
         exclusive_scan(s, L.tile_off, L.tile_off, L.scan_tmp, L.ntiles);
+        if (xg) exclusive_scan(s, L.gtile_off, L.gtile_off, L.scan_tmp, L.ntiles);
         FLIP_LAUNCH_SYNC(k_gmg_row_fill, G, CG_THREADS, s.stream, L.g, (const int *)L.blk_list, (const int *)L.blk_count,
-                         (const float *)L.diag, (const int *)L.tile_off, L.rows, L.rowmap);
+                         (const float *)L.diag, (const int *)L.tile_off, L.rows, L.rowmap, (const int *)L.gtile_off, L.groups);
         FLIP_LAUNCH(k_gmg_ranges, 1, 32, s.stream, (const int *)L.tile_off, L.ntiles, L.g.nbx * L.g.nby,
-                    l < XCH_LEVELS ? cuts : (const Cuts *)nullptr, l, xch_rank(s), L.rng, L.nrows_dev);
+                    l < XCH_LEVELS ? cuts : (const Cuts *)nullptr, l, xch_rank(s), L.rng, L.nrows_dev, (const int *)L.gtile_off, L.grng);
         s.kernel_launches += 4;
         CUDA_CHECK(cudaMemcpyAsync(M.count_host, L.nrows_dev, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CUDA_CHECK(cudaStreamSynchronize(s.stream));
@@ -471,6 +494,10 @@ static void gmg_build(Sim &s, GMG &M) {
             L.cap = (size_t)L.nrows + (size_t)L.nrows / 4 + 1024;
             heap_alloc(s, L.S, L.cap * GMG_STRIDE);   // zero filled: padding slots stay 0
             heap_alloc(s, L.wj, L.cap);
+            // every rank took this branch (same row count).  The zero fill runs on each rank's own stream: no peer may
+            // push rows into the new array before it is done.  A barrier only proves that the peers finished the kernel
+            // BEFORE their previous one, so it takes two to order their fills before this rank's push.
+            if (shard) { xch_barrier(s); xch_barrier(s); }
         }
         // transfer normaliser of the fine level, then the Galerkin product
         FLIP_LAUNCH(k_gmg_pnorm, gmg_grid(s, F), CG_THREADS, s.stream, F.g, (const int *)F.blk_list, (const int *)F.blk_count,
@@ -566,7 +593,10 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         const bool own_restrict = sh && l <= GMG_SHARD_SWEEP_LEVELS + 1 && l < XCH_LEVELS;
         GLevelDev D = gmg_dev(s, L, own), Dr = gmg_dev(s, L, own_restrict);
         int GR = gmg_row_grid(s, L);
-        FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
+        const bool xg = s.mg_xgroup && L.groups != nullptr;   // first explicit level: x-group kernels (gmg.h)
+        const int GX = xg ? gmg_group_grid(s, L) : 0;
+        if (xg) FLIP_LAUNCH_SYNC(k_gmg_restrict_x, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
+        else FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
         if (own) xch_push_halo(s, L.g, L.x[0], sizeof(float), 3, l, 2);
         else if (own_restrict) {
@@ -582,12 +612,14 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         }
         int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre_l[l];
         for (int k = 1; k < sweeps; k++) {
-            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
+            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
         if (l < last) {
-            FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
+            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<2>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, st);
+            else FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
             if (own) xch_push_halo(s, L.g, L.r, sizeof(float), 3, l, 2);
         }
         s.kernel_launches += sweeps + (l < last ? 1 : 0);
@@ -601,8 +633,11 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         // the coarser level is replicated (or, for a sharded one, its ghost planes were pushed after its last sweep)
         FLIP_LAUNCH(k_gmg_prolong, GT, 256, s.stream, D, (const float *)L.pn, M.lv[l + 1].g, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], st);
         if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
+        const bool xg = s.mg_xgroup && L.groups != nullptr;
+        const int GX = xg ? gmg_group_grid(s, L) : 0;
         for (int k = 0; k < M.pre_l[l]; k++) {
-            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
+            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
@@ -676,7 +711,7 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
         mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
-        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma);
+        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma); mix((unsigned long long)s.mg_xgroup);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
             mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
@@ -891,10 +926,15 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
 #endif
         int GR = gmg_row_grid(s, L);
         const float *nof = nullptr;
-        FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[0], L.x[1], nof, M->omega, (const CGState *)nullptr);
+        const bool xg = s.mg_xgroup && L.groups != nullptr;
+        const int GX = xg ? gmg_group_grid(s, L) : 0;
+        auto one = [&](int k) {
+            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, (const CGState *)nullptr);
+            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
+        };
+        one(0);
         CUDA_CHECK(cudaEventRecord(e0, s.stream));
-        for (int k = 0; k < reps; k++)
-            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
+        for (int k = 0; k < reps; k++) one(k);
         CUDA_CHECK(cudaEventRecord(e1, s.stream));
         *alg_bytes = (unsigned long long)L.nrows * (GMG_SLOTS + 5) * 4ull;
     } else if (n == "visc_apply") {

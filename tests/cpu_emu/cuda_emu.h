@@ -44,6 +44,7 @@ struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
 struct double2 { double x, y; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }
 
 typedef int cudaError_t;
