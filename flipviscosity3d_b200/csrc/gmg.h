@@ -30,7 +30,7 @@
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
-#define GMG_XLINES 72      // x-lines of a row's window: 65 for U rows, 51 for V and W rows
+#define GMG_XLINES 88      // x-line entries of a row's window: 65 for U rows, 82 for V and W rows, padded to a multiple of 8
 
 // one axis of the prolongation: fine index n -> up to two coarse indices and weights
 FLIP_D void gmg_parents(bool own, int n, int &p0, int &p1, float &w0, float &w1) {
@@ -795,10 +795,10 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
 #define GMG_XWARPS 4
 #define GMG_XROWS 8
 #define GMG_XSTRIDE 244
-#define GMG_XSMEM (GMG_XWARPS * 2 * GMG_XROWS * GMG_XSTRIDE * 4)
 
-// lines of a row's window, per row component m: {element offset of the line's first slot relative to the row's own
-// cell (column component included), first slot, slots in the line, -}; entry [m][0].w = number of lines
+// line entries of a row's window, per row component m: {element offset of the entry's first slot relative to the row's own
+// cell (column component included), first slot, slots in the entry (<= 4: a 5-slot line is split into 4 + 1), -};
+// entry [m][0].w = number of entries rounded up to a multiple of 8 (the padding entries have 0 slots)
 static inline void gmg_make_lines(const Grid &g, std::vector<int4> &out) {
     int4 z; z.x = z.y = z.z = z.w = 0;
     out.assign(3 * GMG_XLINES, z);
@@ -807,16 +807,17 @@ static inline void gmg_make_lines(const Grid &g, std::vector<int4> &out) {
         for (int mp = 0; mp < 3; mp++) {
             GWin W = gmg_window(m, mp);
             for (int dk = 0; dk < W.n[2]; dk++)
-                for (int dj = 0; dj < W.n[1]; dj++) {
-                    int4 e;
-                    e.x = mp * g.total + W.lo[0] + (W.lo[1] + dj) * SY(g) + (W.lo[2] + dk) * SZ(g);
-                    e.y = W.base + (dk * W.n[1] + dj) * W.n[0];
-                    e.z = W.n[0];
-                    e.w = 0;
-                    out[m * GMG_XLINES + n++] = e;
-                }
+                for (int dj = 0; dj < W.n[1]; dj++)
+                    for (int d0 = 0; d0 < W.n[0]; d0 += 4) {
+                        int4 e;
+                        e.x = mp * g.total + W.lo[0] + d0 + (W.lo[1] + dj) * SY(g) + (W.lo[2] + dk) * SZ(g);
+                        e.y = W.base + (dk * W.n[1] + dj) * W.n[0] + d0;
+                        e.z = W.n[0] - d0 < 4 ? W.n[0] - d0 : 4;
+                        e.w = 0;
+                        out[m * GMG_XLINES + n++] = e;
+                    }
         }
-        out[m * GMG_XLINES].w = n;
+        out[m * GMG_XLINES].w = (n + 7) & ~7;
     }
 }
 
@@ -850,15 +851,12 @@ FLIP_D void gmg_x_wait(unsigned long long *bar, unsigned parity) { gmg_bar_wait(
 #endif
 
 // MODE 1: out = xi + w (b - A xi)   2: out = (b - A xi) / pn.  One warp per x-group; grid-stride over the group range.
+// 35 KB of shared memory per CTA of 4 warps: 6 CTAs = 24 warps per SM, each with one 7.6 KB coefficient block in flight.
 template <int MODE>
 __global__ void __launch_bounds__(32 * GMG_XWARPS) k_gmg_sweep_x(GLevelDev L, const float *__restrict__ b, const float *__restrict__ xi,
                                                                   float *__restrict__ out, const float *__restrict__ pn,
                                                                   const CGState *__restrict__ st) {
-#ifdef FLIP_CPU_EMU
-    __shared__ float Sst[GMG_XWARPS * 2 * GMG_XROWS * GMG_XSTRIDE];
-#else
-    extern __shared__ __align__(128) float Sst[];
-#endif
+    __shared__ __align__(128) float Sst[GMG_XWARPS * GMG_XROWS * GMG_XSTRIDE];
     __shared__ int4 lines[3 * GMG_XLINES];
     __shared__ unsigned long long bars[GMG_XWARPS][2];
     if (st && st->done) return;
@@ -867,39 +865,45 @@ __global__ void __launch_bounds__(32 * GMG_XWARPS) k_gmg_sweep_x(GLevelDev L, co
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     gmg_x_init(bars[wid], lane);
     __syncthreads();
-    float *sbuf[2] = {Sst + (wid * 2 + 0) * GMG_XROWS * GMG_XSTRIDE, Sst + (wid * 2 + 1) * GMG_XROWS * GMG_XSTRIDE};
+    float *sbuf = Sst + wid * GMG_XROWS * GMG_XSTRIDE;
     const int g0 = L.grng[0], g1 = L.grng[1];
     const int nw = gridDim.x * GMG_XWARPS;
     const int T = L.g.total;
     const int xr = lane & 7, d4 = lane >> 3;
-    unsigned phase[2] = {0u, 0u};
-    int buf = 0;
-    int g = g0 + blockIdx.x * GMG_XWARPS + wid;
-    if (g < g1) { const int2 G = L.groups[g]; gmg_x_stage(sbuf[0], L.S, G.x, __popc((unsigned)G.y), &bars[wid][0], lane); }
-    for (; g < g1; g += nw) {
-        const int gn = g + nw;
-        if (gn < g1) { const int2 Gn = L.groups[gn]; gmg_x_stage(sbuf[buf ^ 1], L.S, Gn.x, __popc((unsigned)Gn.y), &bars[wid][buf ^ 1], lane); }
+    unsigned phase = 0u;
+    for (int g = g0 + blockIdx.x * GMG_XWARPS + wid; g < g1; g += nw) {
         const int2 G = L.groups[g];
         const int r0 = G.x;
         const unsigned mask = (unsigned)G.y;
+        gmg_x_stage(sbuf, L.S, r0, __popc(mask), &bars[wid][0], lane);
         const int enc0 = L.rows[r0];
         const int m = enc0 / T;
         const int encb = enc0 - (__ffs(mask) - 1);          // the run's first cell (row component included)
         const bool has = (mask >> xr) & 1u;
         const int rowl = __popc(mask & ((1u << xr) - 1u));
-        const float *__restrict__ xb = xi + (encb - m * T) + xr;
+        const float *__restrict__ xb = xi + (encb - m * T) + xr + d4;
         const int4 *ln = lines + m * GMG_XLINES;
         const int nl = ln[0].w;
-        gmg_x_wait(&bars[wid][buf], phase[buf]);
-        phase[buf] ^= 1u;
-        const float *Sr = sbuf[buf] + rowl * GMG_XSTRIDE;
+        const float *Sr = sbuf + rowl * GMG_XSTRIDE + d4;
         float acc = 0.0f;
-        if (has) {
-#pragma unroll 4
-            for (int l = 0; l < nl; l++) {
-                const int4 e = ln[l];
-                for (int d = d4; d < e.z; d += 4) acc += Sr[e.y + d] * xb[e.x + d];
+        float xv[8];
+        // the gathers of the first batch do not depend on the coefficients: issue them before waiting for the block
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const int4 e = ln[u]; xv[u] = (has && d4 < e.z) ? xb[e.x] : 0.0f; }
+        gmg_x_wait(&bars[wid][0], phase);
+        phase ^= 1u;
+        for (int l0 = 0; l0 < nl; l0 += 8) {
+            float sv[8], xn[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int4 e = ln[l0 + u]; sv[u] = (has && d4 < e.z) ? Sr[e.y] : 0.0f; }
+            if (l0 + 8 < nl) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int4 e = ln[l0 + 8 + u]; xn[u] = (has && d4 < e.z) ? xb[e.x] : 0.0f; }
             }
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc += sv[u] * xv[u];
+#pragma unroll
+            for (int u = 0; u < 8; u++) xv[u] = xn[u];
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
@@ -908,8 +912,7 @@ __global__ void __launch_bounds__(32 * GMG_XWARPS) k_gmg_sweep_x(GLevelDev L, co
             if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
             else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
         }
-        __syncwarp();   // every lane is done with this buffer before the copy after next overwrites it
-        buf ^= 1;
+        __syncwarp();   // every lane is done with the block before the next group's copy overwrites it
     }
     xch_leave(L.X, false);
 }

@@ -10,8 +10,6 @@
     emu::launch((unsigned)(grid), (unsigned)(block), true, [&]() { kernel(__VA_ARGS__); })
 #define FLIP_LAUNCH_X(sync, kernel, grid, block, stream, ...) \
     emu::launch((unsigned)(grid), (unsigned)(block), (sync), [&]() { kernel(__VA_ARGS__); })
-#define FLIP_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
-    emu::launch((unsigned)(grid), (unsigned)(block), true, [&]() { kernel(__VA_ARGS__); })
 #else
 #include <cuda_runtime.h>
 // FLIP_LAUNCH: kernel without intra-block synchronisation; FLIP_LAUNCH_SYNC: kernel that uses
@@ -20,8 +18,6 @@
 #define FLIP_LAUNCH_SYNC(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 // FLIP_LAUNCH_X: kernel whose only block-wide synchronisation is the multi-GPU hand-shake (xch.h); `sync` = handle is sharded
 #define FLIP_LAUNCH_X(sync, kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
-// FLIP_LAUNCH_SMEM: kernel with dynamic shared memory (static arrays in the emulator build)
-#define FLIP_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
 #include <cstdio>

@@ -347,10 +347,6 @@ static GMG *gmg_get(Sim &s) {
     CUDA_CHECK(cudaMallocHost((void **)&M->count_host, 4 * sizeof(int)));
     heap_alloc(s, M->dense, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
     heap_alloc(s, M->Ainv, (size_t)GMG_DENSE_MAX * GMG_DENSE_MAX);
-#ifndef FLIP_CPU_EMU
-    CUDA_CHECK(cudaFuncSetAttribute(k_gmg_sweep_x<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GMG_XSMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_gmg_sweep_x<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GMG_XSMEM));
-#endif
     Grid g = s.g;
     for (int l = 0; l < GMG_MAX_LEVELS; l++) {
         GLevel &L = M->lv[l];
@@ -426,8 +422,8 @@ static int gmg_grid(const Sim &s, const GLevel &L) {
     return L.g.nblocks < G ? L.g.nblocks : G;
 }
 static int gmg_group_grid(const Sim &s, const GLevel &L) {
-    // one warp per x-group (<= 8 rows), GMG_XWARPS warps per CTA, three 61 KB CTAs per SM; sized from the row capacity
-    long long G = cdiv((long long)L.cap / 4 + 1, GMG_XWARPS), cap = s.num_sms * 3;
+    // one warp per x-group (<= 8 rows), GMG_XWARPS warps per CTA, six 35 KB CTAs per SM; sized from the row capacity
+    long long G = cdiv((long long)L.cap / 4 + 1, GMG_XWARPS), cap = s.num_sms * 6;
     return (int)(G < 1 ? 1 : (G > cap ? cap : G));
 }
 static int gmg_row_grid(const Sim &s, const GLevel &L) {
@@ -612,13 +608,13 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         }
         int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre_l[l];
         for (int k = 1; k < sweeps; k++) {
-            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
+            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
             else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
         if (l < last) {
-            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<2>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, st);
+            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<2>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, st);
             else FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
             if (own) xch_push_halo(s, L.g, L.r, sizeof(float), 3, l, 2);
         }
@@ -636,7 +632,7 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         const bool xg = s.mg_xgroup && L.groups != nullptr;
         const int GX = xg ? gmg_group_grid(s, L) : 0;
         for (int k = 0; k < M.pre_l[l]; k++) {
-            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
+            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
             else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
@@ -929,7 +925,7 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         const bool xg = s.mg_xgroup && L.groups != nullptr;
         const int GX = xg ? gmg_group_grid(s, L) : 0;
         auto one = [&](int k) {
-            if (xg) FLIP_LAUNCH_SMEM(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, GMG_XSMEM, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, (const CGState *)nullptr);
+            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, (const CGState *)nullptr);
             else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
         };
         one(0);

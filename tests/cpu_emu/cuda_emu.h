@@ -35,6 +35,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
     unsigned x, y, z;
