@@ -30,7 +30,6 @@
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
-#define GMG_XLINES 88      // x-line entries of a row's window: 65 for U rows, 82 for V and W rows, padded to a multiple of 8
 
 // one axis of the prolongation: fine index n -> up to two coarse indices and weights
 FLIP_D void gmg_parents(bool own, int n, int &p0, int &p1, float &w0, float &w1) {
@@ -105,11 +104,10 @@ struct GLevel {
     float *wj = 0;        // [nrows] smoothing weight per row
     int *offs = 0;        // [3 * GMG_STRIDE] slot -> element offset table (set once: it only depends on the grid)
     // x-groups (first explicit level only): the rows of one 8-wide x-run of a tile (same component, j, k) are consecutive
-    // in `rows`; a group = {first row, 8-bit mask of the cells of the run that are unknowns}.  k_gmg_sweep_x / _restrict_x
+    // in `rows`; a group = {first row, 8-bit mask of the cells of the run that are unknowns}.  k_gmg_restrict_x
     int2 *groups = 0;     // [<= 3T/8]
     int *gtile_off = 0;   // [ntiles + 1] first group of every (plane, tile)
     int *grng = 0;        // device [4]: {first, end} group of this rank's slab, then {0, ngroups}
-    int4 *lines = 0;      // [3 * GMG_XLINES] x-lines of a row's window (set once), gmg_make_lines
     bool owns = false;
 };
 
@@ -140,7 +138,6 @@ struct GLevelDev {
     const int *offs;     // [3 * GMG_STRIDE] element offset of every slot, per row component (0 for padding)
     const int2 *groups;  // x-groups of the level (null: none built)
     const int *grng;     // {first, end} group this launch works on
-    const int4 *lines;
 };
 
 FLIP_D void gmg_unflatten(const Grid &g, int id, int &i, int &j, int &k) {
@@ -781,142 +778,14 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
 }
 #endif
 
-// ---- x-group kernels of the first explicit level --------------------------------------------------------------------
-// The warp-per-row sweep is bound by L1 (ncu: l1tex 79 %, DRAM at half its peak): a row gathers 235 vector values, and
-// the 32 lanes of one load touch ~8 different 128-byte lines (slots run along x for only 3-5 values before they jump to
-// the next j or k).  Here a warp takes a GROUP of up to 8 rows that are neighbours along x (one 8-cell run of a tile,
-// same component, j, k - consecutive rows of the k-plane-major row list) and walks the window LINE by line (a line =
-// the 3-5 slots of one (column component, dj, dk)): lane (xr, d) = (row of the run, offset along x) reads
-// x[i0 + xr + lo + d], so the 32 lanes of a load cover ~12 consecutive floats - one cache line instead of eight.
-// 65 (U rows) or 51 (V, W rows) line loads per group against 8 x 8 row loads of ~8 lines each: ~7x fewer L1 wavefronts,
-// which leaves the coefficient stream as the only bound.  The group's coefficient rows (<= 8 x 960 B, contiguous in S)
-// are staged by TMA bulk copies into shared memory, two groups in flight per warp, one mbarrier per buffer, rows padded
-// to 976 B so that the (xr, d) read pattern is bank-conflict free.
-#define GMG_XWARPS 4
-#define GMG_XROWS 8
-#define GMG_XSTRIDE 244
-
-// line entries of a row's window, per row component m: {element offset of the entry's first slot relative to the row's own
-// cell (column component included), first slot, slots in the entry (<= 4: a 5-slot line is split into 4 + 1), -};
-// entry [m][0].w = number of entries rounded up to a multiple of 8 (the padding entries have 0 slots)
-static inline void gmg_make_lines(const Grid &g, std::vector<int4> &out) {
-    int4 z; z.x = z.y = z.z = z.w = 0;
-    out.assign(3 * GMG_XLINES, z);
-    for (int m = 0; m < 3; m++) {
-        int n = 0;
-        for (int mp = 0; mp < 3; mp++) {
-            GWin W = gmg_window(m, mp);
-            for (int dk = 0; dk < W.n[2]; dk++)
-                for (int dj = 0; dj < W.n[1]; dj++)
-                    for (int d0 = 0; d0 < W.n[0]; d0 += 4) {
-                        int4 e;
-                        e.x = mp * g.total + W.lo[0] + d0 + (W.lo[1] + dj) * SY(g) + (W.lo[2] + dk) * SZ(g);
-                        e.y = W.base + (dk * W.n[1] + dj) * W.n[0] + d0;
-                        e.z = W.n[0] - d0 < 4 ? W.n[0] - d0 : 4;
-                        e.w = 0;
-                        out[m * GMG_XLINES + n++] = e;
-                    }
-        }
-        out[m * GMG_XLINES].w = (n + 7) & ~7;
-    }
-}
-
-#ifdef FLIP_CPU_EMU
-FLIP_D void gmg_x_init(unsigned long long *, int) {}
-FLIP_D void gmg_x_stage(float *dst, const float *S, int r0, int cnt, unsigned long long *, int lane) {
-    for (int row = 0; row < cnt; row++)
-        for (int q = lane; q < GMG_STRIDE; q += 32) dst[row * GMG_XSTRIDE + q] = S[(size_t)(r0 + row) * GMG_STRIDE + q];
-    __syncwarp();
-}
-FLIP_D void gmg_x_wait(unsigned long long *, unsigned) { __syncwarp(); }
-#else
-FLIP_D void gmg_x_init(unsigned long long *bar, int lane) {
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(bar)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(bar + 1)) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-}
-// lane 0 announces the bytes, lanes < cnt issue one 960-byte bulk copy each (global -> shared, completion on the mbarrier)
-FLIP_D void gmg_x_stage(float *dst, const float *S, int r0, int cnt, unsigned long long *bar, int lane) {
-    if (lane == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gmg_smem(bar)), "r"((unsigned)(cnt * GMG_STRIDE * 4)) : "memory");
-    __syncwarp();
-    if (lane < cnt)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gmg_smem(dst + lane * GMG_XSTRIDE)),
-                     "l"(S + (size_t)(r0 + lane) * GMG_STRIDE), "r"((unsigned)(GMG_STRIDE * 4)), "r"(gmg_smem(bar))
-                     : "memory");
-}
-FLIP_D void gmg_x_wait(unsigned long long *bar, unsigned parity) { gmg_bar_wait(bar, parity); }
-#endif
-
-// MODE 1: out = xi + w (b - A xi)   2: out = (b - A xi) / pn.  One warp per x-group; grid-stride over the group range.
-// 35 KB of shared memory per CTA of 4 warps: 6 CTAs = 24 warps per SM, each with one 7.6 KB coefficient block in flight.
-template <int MODE>
-__global__ void __launch_bounds__(32 * GMG_XWARPS) k_gmg_sweep_x(GLevelDev L, const float *__restrict__ b, const float *__restrict__ xi,
-                                                                  float *__restrict__ out, const float *__restrict__ pn,
-                                                                  const CGState *__restrict__ st) {
-    __shared__ __align__(128) float Sst[GMG_XWARPS * GMG_XROWS * GMG_XSTRIDE];
-    __shared__ int4 lines[3 * GMG_XLINES];
-    __shared__ unsigned long long bars[GMG_XWARPS][2];
-    if (st && st->done) return;
-    if (!xch_enter(L.X, L.X.nbr != 0)) return;
-    for (int q = threadIdx.x; q < 3 * GMG_XLINES; q += blockDim.x) lines[q] = L.lines[q];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    gmg_x_init(bars[wid], lane);
-    __syncthreads();
-    float *sbuf = Sst + wid * GMG_XROWS * GMG_XSTRIDE;
-    const int g0 = L.grng[0], g1 = L.grng[1];
-    const int nw = gridDim.x * GMG_XWARPS;
-    const int T = L.g.total;
-    const int xr = lane & 7, d4 = lane >> 3;
-    unsigned phase = 0u;
-    for (int g = g0 + blockIdx.x * GMG_XWARPS + wid; g < g1; g += nw) {
-        const int2 G = L.groups[g];
-        const int r0 = G.x;
-        const unsigned mask = (unsigned)G.y;
-        gmg_x_stage(sbuf, L.S, r0, __popc(mask), &bars[wid][0], lane);
-        const int enc0 = L.rows[r0];
-        const int m = enc0 / T;
-        const int encb = enc0 - (__ffs(mask) - 1);          // the run's first cell (row component included)
-        const bool has = (mask >> xr) & 1u;
-        const int rowl = __popc(mask & ((1u << xr) - 1u));
-        const float *__restrict__ xb = xi + (encb - m * T) + xr + d4;
-        const int4 *ln = lines + m * GMG_XLINES;
-        const int nl = ln[0].w;
-        const float *Sr = sbuf + rowl * GMG_XSTRIDE + d4;
-        float acc = 0.0f;
-        float xv[8];
-        // the gathers of the first batch do not depend on the coefficients: issue them before waiting for the block
-#pragma unroll
-        for (int u = 0; u < 8; u++) { const int4 e = ln[u]; xv[u] = (has && d4 < e.z) ? xb[e.x] : 0.0f; }
-        gmg_x_wait(&bars[wid][0], phase);
-        phase ^= 1u;
-        for (int l0 = 0; l0 < nl; l0 += 8) {
-            float sv[8], xn[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { const int4 e = ln[l0 + u]; sv[u] = (has && d4 < e.z) ? Sr[e.y] : 0.0f; }
-            if (l0 + 8 < nl) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) { const int4 e = ln[l0 + 8 + u]; xn[u] = (has && d4 < e.z) ? xb[e.x] : 0.0f; }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) acc += sv[u] * xv[u];
-#pragma unroll
-            for (int u = 0; u < 8; u++) xv[u] = xn[u];
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (has && d4 == 0) {
-            const int enc = encb + xr, r = r0 + rowl;
-            if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
-            else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
-        }
-        __syncwarp();   // every lane is done with the block before the next group's copy overwrites it
-    }
-    xch_leave(L.X, false);
-}
-
+// ---- x-groups of the first explicit level ---------------------------------------------------------------------------
+// A group = the rows of one 8-cell x-run of a tile (same component, j, k): consecutive rows of the k-plane-major row
+// list, {first row, 8-bit mask of the cells that are unknowns}.  The restriction from level 0 runs over groups: lane
+// (xr, a) = (coarse row of the run, child offset along x), so the 32 lanes of a load read 18 consecutive fine values
+// (one or two cache lines) where the warp-per-row kernel touches 8 scattered lines: 85 -> 29 us at 256^3 on B200.
+// The same lane mapping was tried for the Jacobi sweeps (a warp walks the 65-82 x-lines of a group's window, coefficient
+// blocks staged by TMA): 116 us against 80 us for the warp-per-row sweep below - with one 7.6 KB coefficient block per
+// warp the SM holds 24 warps, too few to hide the latency of ~10 dependent load batches per group.  Not kept.
 // coarse b = P^T r / 8 and the first sweep from zero (k_gmg_restrict_first) over the x-groups of the coarse level: lane
 // (xr, a) reads fine x = 2 (i0 + xr) - 1 + a of every (fj, fk) line of the 4 x 4 children box, so a load covers 18
 // consecutive fine values instead of 8 scattered lines

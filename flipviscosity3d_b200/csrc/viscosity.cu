@@ -373,14 +373,10 @@ static GMG *gmg_get(Sim &s) {
             for (int m = 0; m < 3; m++)
                 for (int slot = 0; slot < GMG_SLOTS; slot++) offs[m * GMG_STRIDE + slot] = gmg_slot_offset(g, m, slot);
             CUDA_CHECK(cudaMemcpyAsync(L.offs, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice, s.stream));
-            std::vector<int4> lines;
-            if (l == 1) {   // x-groups: the first explicit level is the one whose sweeps matter (gmg.h k_gmg_sweep_x)
+            if (l == 1) {   // x-groups: the restriction from level 0 is the expensive one (gmg.h k_gmg_restrict_x)
                 heap_alloc(s, L.groups, 3 * T / 8 + 8);
                 heap_alloc(s, L.gtile_off, (size_t)L.ntiles + 1);
                 heap_alloc(s, L.grng, 4);
-                heap_alloc(s, L.lines, 3 * GMG_XLINES);
-                gmg_make_lines(g, lines);
-                CUDA_CHECK(cudaMemcpyAsync(L.lines, lines.data(), lines.size() * sizeof(int4), cudaMemcpyHostToDevice, s.stream));
             }
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
             L.owns = true;
@@ -411,7 +407,7 @@ static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
     GLevelDev d;
     d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
     d.rng = own ? L.rng : L.rng + 2;
-    d.groups = L.groups; d.lines = L.lines;
+    d.groups = L.groups;
     d.grng = L.grng ? (own ? L.grng : L.grng + 2) : nullptr;
     d.X = xch_of(s);
     if (!own) d.X.nranks = 1;
@@ -420,11 +416,6 @@ static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
 static int gmg_grid(const Sim &s, const GLevel &L) {
     int G = cg_grid(s);
     return L.g.nblocks < G ? L.g.nblocks : G;
-}
-static int gmg_group_grid(const Sim &s, const GLevel &L) {
-    // one warp per x-group (<= 8 rows), GMG_XWARPS warps per CTA, six 35 KB CTAs per SM; sized from the row capacity
-    long long G = cdiv((long long)L.cap / 4 + 1, GMG_XWARPS), cap = s.num_sms * 6;
-    return (int)(G < 1 ? 1 : (G > cap ? cap : G));
 }
 static int gmg_row_grid(const Sim &s, const GLevel &L) {
     // one warp per row, 8 warps per CTA.  Sized from the row CAPACITY (which only changes when the level is
@@ -589,8 +580,7 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         const bool own_restrict = sh && l <= GMG_SHARD_SWEEP_LEVELS + 1 && l < XCH_LEVELS;
         GLevelDev D = gmg_dev(s, L, own), Dr = gmg_dev(s, L, own_restrict);
         int GR = gmg_row_grid(s, L);
-        const bool xg = s.mg_xgroup && L.groups != nullptr;   // first explicit level: x-group kernels (gmg.h)
-        const int GX = xg ? gmg_group_grid(s, L) : 0;
+        const bool xg = s.mg_xgroup && L.groups != nullptr;   // first explicit level: restriction over x-groups (gmg.h)
         if (xg) FLIP_LAUNCH_SYNC(k_gmg_restrict_x, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         else FLIP_LAUNCH_SYNC(k_gmg_restrict_first, GR, 256, s.stream, Dr, M.lv[l - 1].g, (const float *)M.lv[l - 1].r, L.b, L.x[0], st);
         cur[l] = 0;
@@ -608,14 +598,12 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         }
         int sweeps = l == last ? 1 + M.coarse_sweeps : M.pre_l[l];
         for (int k = 1; k < sweeps; k++) {
-            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
-            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
         if (l < last) {
-            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<2>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, st);
-            else FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
+            FLIP_LAUNCH_SYNC(sweep2, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.r, (const float *)L.pn, w, st);
             if (own) xch_push_halo(s, L.g, L.r, sizeof(float), 3, l, 2);
         }
         s.kernel_launches += sweeps + (l < last ? 1 : 0);
@@ -629,11 +617,8 @@ static void gmg_vcycle(Sim &s, GMG &M, const double *r_in, double *z_out, const 
         // the coarser level is replicated (or, for a sharded one, its ghost planes were pushed after its last sweep)
         FLIP_LAUNCH(k_gmg_prolong, GT, 256, s.stream, D, (const float *)L.pn, M.lv[l + 1].g, (const float *)M.lv[l + 1].x[cur[l + 1]], L.x[cur[l]], st);
         if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
-        const bool xg = s.mg_xgroup && L.groups != nullptr;
-        const int GX = xg ? gmg_group_grid(s, L) : 0;
         for (int k = 0; k < M.pre_l[l]; k++) {
-            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, st);
-            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[cur[l]], L.x[cur[l] ^ 1], nof, w, st);
             cur[l] ^= 1;
             if (own) xch_push_halo(s, L.g, L.x[cur[l]], sizeof(float), 3, l, 2);
         }
@@ -922,11 +907,8 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
 #endif
         int GR = gmg_row_grid(s, L);
         const float *nof = nullptr;
-        const bool xg = s.mg_xgroup && L.groups != nullptr;
-        const int GX = xg ? gmg_group_grid(s, L) : 0;
         auto one = [&](int k) {
-            if (xg) FLIP_LAUNCH_SYNC(k_gmg_sweep_x<1>, GX, 32 * GMG_XWARPS, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, (const CGState *)nullptr);
-            else FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
+            FLIP_LAUNCH_SYNC(sweep1, GR, 256, s.stream, D, (const float *)L.b, (const float *)L.x[k & 1], L.x[(k & 1) ^ 1], nof, M->omega, (const CGState *)nullptr);
         };
         one(0);
         CUDA_CHECK(cudaEventRecord(e0, s.stream));
