@@ -1,7 +1,9 @@
 """Stage parity in the regime the benchmark is quoted on (dt*mu/dx^2 ~ 3300: 256^3 at viscosity 5), teacher forced against
 the oracle's raised-cap solves ("truncated reference solves").  The 128^3 / viscosity-20 fixture has
 the same stiffness as 256^3 / viscosity 5 and is what the regular -m gpu suite runs; the 256^3 fixture itself is checked
-when present (tests/golden_big/ is generated on the CPU by tests/golden/make_parity_big.py and is git-ignored).
+when present.  Both are generated on the CPU by tests/golden/make_parity_big.py; the 128^3 fixture (5 MB) is committed
+under tests/golden/, the 256^3 one (35 MB) lives in the git-ignored tests/golden_big/ and its result is kept in
+profiles/r2_parity_256_mu5.json.
 
 Tolerances (velocities: max |u| ~ 0.2 here), on the faces bordering fluid:
   * library with the reference's own rows (viscosity_operator = 1: the fp32-rounded diagonal of
@@ -36,7 +38,9 @@ def _check(res):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["parity_128_mu20.npz", "parity_256_mu5.npz"])
 def test_stage_parity_in_bench_regime(cuda_lib, name):
-    path = os.path.join(BIG, name)
+    path = os.path.join(common.ROOT, "tests", "golden", name)     # committed fixture
+    if not os.path.exists(path):
+        path = os.path.join(BIG, name)                           # generated locally (git-ignored)
     if not os.path.exists(path):
         pytest.skip("fixture %s not generated (tests/golden/make_parity_big.py)" % name)
     import parity_big
