@@ -7,12 +7,13 @@ import sys
 KEEP = ["Kernel Name", "Block Size", "Grid Size",
         "gpu__time_duration.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed.sum", "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor"]

@@ -728,8 +728,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     __shared__ int offs[3][GMG_STRIDE];
     __shared__ __align__(128) float Srow[8][2][GMG_STRIDE];
     __shared__ __align__(8) unsigned long long bars[8][2];
-    if (st && st->done) return;
-    if (!xch_enter(L.X, L.X.nbr != 0)) return;
+    // the table loads are issued before the done flag is read: two global-memory latencies overlap instead of adding up
     for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
@@ -737,6 +736,8 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(&bars[wid][1])) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy sees the initialised barriers
     }
+    if (st && st->done) return;
+    if (!xch_enter(L.X, L.X.nbr != 0)) return;
     __syncthreads();
     const int r0 = L.rng[0], r1 = L.rng[1];
     const int nwarps = gridDim.x * (blockDim.x >> 5);
