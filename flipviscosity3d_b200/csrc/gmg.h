@@ -641,6 +641,21 @@ FLIP_HD int gmg_slot_offset(const Grid &g, int m, int slot) {
     return 0;
 }
 
+// Prologue loads of the multigrid kernels.  The coarse levels are latency bound (a few thousand rows: one kernel = a
+// chain of dependent global loads, ~0.7 us each), so the values that do not depend on each other - the CG's done flag, the
+// row range / cell count, the offset table - are requested together, pinned in program order by volatile asm (the
+// compiler otherwise sinks them behind the early return), instead of one round trip after the other.
+#ifdef FLIP_CPU_EMU
+FLIP_D int ld_early(const int *p) { return *p; }
+#else
+FLIP_D int ld_early(const int *p) {
+    int v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#endif
+FLIP_D int ld_done(const CGState *st) { return st ? ld_early(&st->done) : 0; }
+
 // one warp: row r of an explicit level.  MODE 1: out = xi + w (b - A xi)   2: out = (b - A xi) / pn.
 // offs: the level's slot -> element offset table [3][GMG_STRIDE] (shared or global memory)
 // L2: the vectors are read with L2-only loads (persistent kernels: other CTAs wrote them earlier in the same launch, and
@@ -728,7 +743,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     __shared__ int offs[3][GMG_STRIDE];
     __shared__ __align__(128) float Srow[8][2][GMG_STRIDE];
     __shared__ __align__(8) unsigned long long bars[8][2];
-    // the table loads are issued before the done flag is read: two global-memory latencies overlap instead of adding up
+    const int done = ld_done(st), r0 = ld_early(L.rng), r1 = ld_early(L.rng + 1);
     for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
@@ -736,10 +751,9 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(&bars[wid][1])) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy sees the initialised barriers
     }
-    if (st && st->done) return;
+    if (done) return;
     if (!xch_enter(L.X, L.X.nbr != 0)) return;
     __syncthreads();
-    const int r0 = L.rng[0], r1 = L.rng[1];
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     int r = r0 + blockIdx.x * (blockDim.x >> 5) + wid;
     unsigned phase[2] = {0u, 0u};
@@ -792,9 +806,9 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
 // consecutive fine values instead of 8 scattered lines
 __global__ void __launch_bounds__(256) k_gmg_restrict_x(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
                                                          float *__restrict__ x0, const CGState *__restrict__ st) {
-    if (st && st->done) return;
+    const int done = ld_done(st), g0 = ld_early(C.grng), g1 = ld_early(C.grng + 1);
+    if (done) return;
     if (!xch_enter(C.X, C.X.nbr != 0)) return;
-    const int g0 = C.grng[0], g1 = C.grng[1];
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     const int T = C.g.total;
@@ -854,13 +868,13 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_gmg0_sweep(G0Params L, const double *__restrict__ b, const float *__restrict__ xi,
                                                      float *__restrict__ out, double *__restrict__ zout, float omega,
                                                      const CGState *__restrict__ st) {
-    if (st && st->done) return;
+    const int done = ld_done(st), nc = ld_early(L.cell_count);
+    if (done) return;
     if (MODE != 0 && !xch_enter(L.X, L.X.nbr != 0)) return;   // mode 0 reads and writes this rank's own cells only
     const Grid &g = L.g;
     const int sy = SY(g), sz = SZ(g);
     const size_t T = (size_t)g.total;
     const float *__restrict__ cc = L.coef, *__restrict__ cu = L.coef + T, *__restrict__ cv = L.coef + 2 * T, *__restrict__ cw = L.coef + 3 * T;
-    const int nc = *L.cell_count;
     for (int qq = blockIdx.x * blockDim.x + threadIdx.x; qq < nc; qq += gridDim.x * blockDim.x) {
         const int id = L.cell_list[qq];
         const float dU = L.diag[id], dV = L.diag[T + id], dW = L.diag[2 * T + id];
@@ -943,11 +957,11 @@ FLIP_D float gmg_interp(int m, int i, int j, int k, const Grid &gc, const float 
 // level 0: x += P x_c on the cell list
 __global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const float *__restrict__ xc, float *__restrict__ xf,
                                                        const CGState *__restrict__ st) {
-    if (st && st->done) return;
+    const int done = ld_done(st), nc = ld_early(F.cell_count);
+    if (done) return;
     if (!xch_enter(F.X, F.X.nbr != 0)) return;
     const Grid &g = F.g;
     const size_t T = (size_t)g.total;
-    const int nc = *F.cell_count;
     for (int qq = blockIdx.x * blockDim.x + threadIdx.x; qq < nc; qq += gridDim.x * blockDim.x) {
         const int id = F.cell_list[qq];
         int i, j, k;
@@ -963,8 +977,8 @@ __global__ void __launch_bounds__(256) k_gmg0_prolong(G0Params F, Grid gc, const
 // explicit levels: x += P x_c, one thread per fine row
 __global__ void __launch_bounds__(256) k_gmg_prolong(GLevelDev F, const float *__restrict__ pn, Grid gc, const float *__restrict__ xc,
                                                       float *__restrict__ xf, const CGState *__restrict__ st) {
-    if (st && st->done) return;
-    const int r0 = F.rng[0], r1 = F.rng[1];
+    const int done = ld_done(st), r0 = ld_early(F.rng), r1 = ld_early(F.rng + 1);
+    if (done) return;
     for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < r1; r += gridDim.x * blockDim.x) {
         int enc = F.rows[r];
         int m = enc / F.g.total, id = enc - m * F.g.total;
@@ -1011,9 +1025,9 @@ FLIP_D void gmg_row_restrict(const Grid &gc, const int *__restrict__ rows, const
 
 __global__ void __launch_bounds__(256) k_gmg_restrict_first(GLevelDev C, Grid gf, const float *__restrict__ rf, float *__restrict__ bc,
                                                              float *__restrict__ x0, const CGState *__restrict__ st) {
-    if (st && st->done) return;
+    const int done = ld_done(st), r0 = ld_early(C.rng), r1 = ld_early(C.rng + 1);
+    if (done) return;
     if (!xch_enter(C.X, C.X.nbr != 0)) return;
-    const int r0 = C.rng[0], r1 = C.rng[1];
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     for (int r = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < r1; r += nwarps)
@@ -1074,8 +1088,8 @@ __global__ void __launch_bounds__(1024) k_gmg_dense_inverse(GLevelDev L, const i
 // x = A^-1 b on the coarsest level, one warp per row
 __global__ void __launch_bounds__(256) k_gmg_dense_apply(GLevelDev L, const float *__restrict__ Ainv, const float *__restrict__ b,
                                                           float *__restrict__ x, const CGState *__restrict__ st) {
-    if (st && st->done) return;
-    const int n = *L.nrows;
+    const int done = ld_done(st), n = ld_early(L.nrows);
+    if (done) return;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {

@@ -1,7 +1,8 @@
 """BASELINE.json configs as parity cases on the real device (-m gpu), against the compiled reference.
 
 configs[0] bunny in sphere 64^3 (the reference's shipped scene), configs[1] cube dam-break 128^3
-viscosity 0 (pressure PCG only), configs[2] rod 128^3 high viscosity.  One full frame each through
+viscosity 0 (pressure PCG only), configs[2] rod 128^3 high viscosity, configs[4] viscous sheet at 96^3 (the 512^3
+size itself is a bench line: profiles/r2_sheet512_*.json).  Two full frames each through
 the public advance() path, plus size-independent properties at the bench size (256^3): particles
 stay inside the inset domain box, no NaNs, solves converge, the run is bit-reproducible.
 """
@@ -26,6 +27,7 @@ def _scene(n, liquid, boundary):
     ("config0_bunny64_visc5", 64, "stanford_bunny", "sphere_large", 5.0, 2, 2e-5),
     ("config1_cube128_visc0", 128, "cube", None, 0.0, 2, 2e-5),
     ("config2_rod128_visc50", 128, "rod", None, 50.0, 2, 2e-5),
+    ("config4_sheet96_visc5", 96, "sheet", None, 5.0, 2, 2e-5),      # configs[4] at reduced size (512^3 there: bench.py --scene sheet --size 512)
 ])
 def test_config_frames_match_reference(cuda_lib, oracle, name, n, liquid, boundary, visc, frames, tol):
     phi, p = _scene(n, liquid, boundary)
