@@ -17,7 +17,7 @@ substeps in order: warm-up = substeps 1..W, timed = substeps W+1..W+K.
             buffers: every step uploads the particles (flip_set_particles), runs the substep and reads them back
             (flip_get_particles); the final particles must equal the resident run's bit for bit
   roofline  dominant kernel = the Jacobi sweep on the first explicit level of the Galerkin multigrid that preconditions
-            the viscosity CG (k_gmg_sweep<1>): algorithmic bytes = rows x (stored coefficients + row index + weight + b
+            the viscosity CG (k_gmg_sweep_tma<1>): algorithmic bytes = rows x (stored coefficients + row index + weight + b
             + x in + x out) x 4 B, divided by its average launch duration measured with CUDA events on the library's
             stream (flip_time_kernel) right after the timed region, on the hierarchy of the last timed substep;
             `stages` holds the same arithmetic for every stage in SURVEY.md 8(d) units
@@ -504,7 +504,8 @@ def run_b200(args):
     try:
         k_ms, k_bytes = sim.time_kernel("gmg_sweep_l1", 40)
         a_ms, a_bytes = sim.time_kernel("visc_apply", 40)
-        roof = {"bound": "hbm", "kernel": "k_gmg_sweep<1> on multigrid level 1 (Jacobi sweep over explicit Galerkin rows, one warp per row)",
+        roof = {"bound": "hbm", "kernel": "k_gmg_sweep_tma<1> on multigrid level 1 (Jacobi sweep over explicit Galerkin rows, one warp per row, "
+                          "coefficient rows staged by cp.async.bulk)",
                 "achieved": k_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_kind": peak_kind,
                 "ms_per_launch": k_ms, "algorithmic_bytes_per_launch": k_bytes, "traffic": ncu_traffic("gmg_sweep_l1"),
                 "other_kernels": {"k_visc_apply": {"ms_per_launch": a_ms, "algorithmic_bytes_per_launch": a_bytes,
