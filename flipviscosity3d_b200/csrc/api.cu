@@ -31,7 +31,7 @@ void sim_alloc(Sim &s, int ni, int nj, int nk, float dx) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     // Heap sizing: the fixed fields below take ~330 B per padded cell, the multigrid vectors ~70 B more; particles and
     // the explicit multigrid rows come on top.  Later needs grow the heap by further chunks (until the peers map it).
-    s.heap.first_chunk = (size_t)520 * T + ((size_t)64 << 20);
+    s.heap.first_chunk = (size_t)540 * T + ((size_t)64 << 20);
     s.heap.grow_chunk = (size_t)130 * T + ((size_t)64 << 20);
     // _particleRadius = (float)(_dx * 1.01*sqrt(3.0)/2.0)  (src/fluidsimulation.cpp:36)
     s.particle_radius = (float)((double)dx * 1.01 * sqrt(3.0) / 2.0);
@@ -660,6 +660,7 @@ int flip_set_param(flip_sim *h, const char *name, double value) {
     else if (n == "mg_dense") s.mg_dense = (int)value;
     else if (n == "mg_build") s.mg_build = (int)value;
     else if (n == "mg_xgroup") s.mg_xgroup = (int)value;
+    else if (n == "mg_compact") s.mg_compact = (int)value;
     else if (n == "pressure_resident") s.pres_resident = (int)value;
     else if (n == "mg_dense_rows") s.mg_dense_rows = (int)value;
     else if (n == "mg_sweeps_l0") s.mg_sweeps_l0 = (int)value;

@@ -30,6 +30,7 @@
 #define GMG_MAX_LEVELS 8
 #define GMG_SLOTS 235
 #define GMG_STRIDE 240     // floats per stored row (235 slots + zero padding; 960 B)
+#define GMG_CSTRIDE 160    // floats per COMPACT row of the first explicit level (see k_gmg_compact_rows; 640 B)
 
 // one axis of the prolongation: fine index n -> up to two coarse indices and weights
 FLIP_D void gmg_parents(bool own, int n, int &p0, int &p1, float &w0, float &w1) {
@@ -103,6 +104,12 @@ struct GLevel {
     float *S = 0;         // [nrows * GMG_STRIDE]
     float *wj = 0;        // [nrows] smoothing weight per row
     int *offs = 0;        // [3 * GMG_STRIDE] slot -> element offset table (set once: it only depends on the grid)
+    // compact rows (first explicit level only, k_gmg_compact_rows): the sweeps read these instead of S
+    float *Sc = 0;        // [nrows * GMG_CSTRIDE]
+    int *coffs = 0;       // [3 * GMG_CSTRIDE] compact slot -> element offset
+    int *cslot = 0;       // [3 * GMG_CSTRIDE] compact slot -> slot of the full row (-1: padding)
+    int *cmeta = 0;       // [4] {compact rows valid for this solve, kept slots of component 0, 1, 2}
+    unsigned *cmask = 0;  // [3 * 8] union over the rows of a component of their non-zero slots
     // x-groups (first explicit level only): the rows of one 8-wide x-run of a tile (same component, j, k) are consecutive
     // in `rows`; a group = {first row, 8-bit mask of the cells of the run that are unknowns}.  k_gmg_restrict_x
     int2 *groups = 0;     // [<= 3T/8]
@@ -136,6 +143,9 @@ struct GLevelDev {
     const float *S;
     const float *wj;     // [nrows] smoothing weights
     const int *offs;     // [3 * GMG_STRIDE] element offset of every slot, per row component (0 for padding)
+    const float *Sc;     // compact rows / table / flag of the level, or null (then the sweeps read S)
+    const int *coffs;
+    const int *cmeta;
     const int2 *groups;  // x-groups of the level (null: none built)
     const int *grng;     // {first, end} group this launch works on
 };
@@ -661,18 +671,19 @@ FLIP_D int ld_done(const CGState *st) { return st ? ld_early(&st->done) : 0; }
 // L2: the vectors are read with L2-only loads (persistent kernels: other CTAs wrote them earlier in the same launch, and
 // loads through const __restrict__ pointers may take the non-coherent path, which a fence does not invalidate)
 template <int MODE, bool L2 = false>
-FLIP_D void gmg_row_apply(const Grid &g, const int *__restrict__ rows, const float *__restrict__ S, const float *__restrict__ wj,
-                          const float *b, const float *xi, float *out, const float *__restrict__ pn, const int *offs, int r, int lane) {
+FLIP_D void gmg_row_apply(const Grid &g, const int *__restrict__ rows, const float *__restrict__ S, int stride,
+                          const float *__restrict__ wj, const float *b, const float *xi, float *out, const float *__restrict__ pn,
+                          const int *offs, int r, int lane) {
     const int enc = rows[r];
     const int m = enc / g.total, id = enc - m * g.total;
-    const float *__restrict__ Sr = S + (size_t)r * GMG_STRIDE;
+    const float *__restrict__ Sr = S + (size_t)r * stride;   // stride: GMG_STRIDE, or GMG_CSTRIDE for compact rows
     const float *xc = xi + id;
-    const int *om = offs + m * GMG_STRIDE;
+    const int *om = offs + m * GMG_STRIDE;                   // the shared table keeps its pitch
     float acc = 0.0f;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         int slot = lane + 32 * t;
-        if (slot < GMG_STRIDE) acc += Sr[slot] * (L2 ? ld_cg(xc + om[slot]) : xc[om[slot]]);
+        if (slot < stride) acc += Sr[slot] * (L2 ? ld_cg(xc + om[slot]) : xc[om[slot]]);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
@@ -691,8 +702,12 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
     __shared__ int offs[3][GMG_STRIDE];
     if (st && st->done) return;
     if (!xch_enter(L.X, L.X.nbr != 0)) return;
+    const bool compact = L.cmeta != nullptr && L.cmeta[0] != 0;
+    const int stride = compact ? GMG_CSTRIDE : GMG_STRIDE;
+    const float *__restrict__ Sb = compact ? L.Sc : L.S;
     if (MODE != 0) {
-        for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
+        const int *__restrict__ ot = compact ? L.coffs : L.offs;
+        for (int q = threadIdx.x; q < 3 * stride; q += blockDim.x) offs[q / stride][q % stride] = ot[q];
         __syncthreads();
     }
     const int r0 = L.rng[0], r1 = L.rng[1];
@@ -703,7 +718,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep(GLevelDev L, const float *__r
             if (lane == 0) { int enc = L.rows[r]; out[enc] = L.wj[r] * b[enc]; }
             continue;
         }
-        gmg_row_apply<MODE == 2 ? 2 : 1>(L.g, L.rows, L.S, L.wj, b, xi, out, pn, &offs[0][0], r, lane);
+        gmg_row_apply<MODE == 2 ? 2 : 1>(L.g, L.rows, Sb, stride, L.wj, b, xi, out, pn, &offs[0][0], r, lane);
     }
     xch_leave(L.X, false);
 }
@@ -744,7 +759,14 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     __shared__ __align__(128) float Srow[8][2][GMG_STRIDE];
     __shared__ __align__(8) unsigned long long bars[8][2];
     const int done = ld_done(st), r0 = ld_early(L.rng), r1 = ld_early(L.rng + 1);
-    for (int q = threadIdx.x; q < 3 * GMG_STRIDE; q += blockDim.x) (&offs[0][0])[q] = L.offs[q];
+    const bool compact = L.cmeta != nullptr && ld_early(L.cmeta) != 0;
+    const int stride = compact ? GMG_CSTRIDE : GMG_STRIDE;
+    const float *__restrict__ Sb = compact ? L.Sc : L.S;
+    const unsigned row_bytes = (unsigned)stride * 4u;
+    {
+        const int *__restrict__ ot = compact ? L.coffs : L.offs;
+        for (int q = threadIdx.x; q < 3 * stride; q += blockDim.x) offs[q / stride][q % stride] = ot[q];
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gmg_smem(&bars[wid][0])) : "memory");
@@ -758,10 +780,10 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     int r = r0 + blockIdx.x * (blockDim.x >> 5) + wid;
     unsigned phase[2] = {0u, 0u};
     int buf = 0;
-    if (r < r1 && lane == 0) gmg_bulk_load(Srow[wid][0], L.S + (size_t)r * GMG_STRIDE, GMG_STRIDE * 4, &bars[wid][0]);
+    if (r < r1 && lane == 0) gmg_bulk_load(Srow[wid][0], Sb + (size_t)r * stride, row_bytes, &bars[wid][0]);
     for (; r < r1; r += nwarps) {
         const int rn = r + nwarps;
-        if (rn < r1 && lane == 0) gmg_bulk_load(Srow[wid][buf ^ 1], L.S + (size_t)rn * GMG_STRIDE, GMG_STRIDE * 4, &bars[wid][buf ^ 1]);
+        if (rn < r1 && lane == 0) gmg_bulk_load(Srow[wid][buf ^ 1], Sb + (size_t)rn * stride, row_bytes, &bars[wid][buf ^ 1]);
         const int enc = L.rows[r];
         const int m = enc / L.g.total, id = enc - m * L.g.total;
         const float *__restrict__ xc = xi + id;
@@ -770,7 +792,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const int slot = lane + 32 * t;
-            xv[t] = slot < GMG_STRIDE ? xc[offs[m][slot]] : 0.0f;
+            xv[t] = slot < stride ? xc[offs[m][slot]] : 0.0f;
         }
         gmg_bar_wait(&bars[wid][buf], phase[buf]);
         phase[buf] ^= 1u;
@@ -779,7 +801,7 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const int slot = lane + 32 * t;
-            if (slot < GMG_STRIDE) acc += Sr[slot] * xv[t];
+            if (slot < stride) acc += Sr[slot] * xv[t];
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
@@ -792,6 +814,83 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     xch_leave(L.X, false);
 }
 #endif
+
+// ---- compact rows of the first explicit level ------------------------------------------------------------------------
+// Level 1 is the Galerkin product of the level-0 STENCIL, which is much sparser than a general row of the hierarchy: at
+// most 159 of its 235 slots are ever non-zero, the same ones for every row of a component (measured with
+// dev/gmg_fill.py; deeper levels fill all 235).  After the set-up the rows of that level are therefore copied into a second
+// array with GMG_CSTRIDE = 160 slots per row (640 bytes: one bulk copy) and their own slot -> offset table, and the sweeps
+// read those: a third fewer coefficient bytes and - what bounds the kernel - a third fewer gathers per row.  The kept slots
+// are found on the device for every solve (union of the non-zero slots over the rows of a component); should a component
+// ever need more than GMG_CSTRIDE, cmeta[0] stays 0 and the sweeps keep reading the full rows.  The full rows stay what the
+// set-up of the next level, the mirror pass and the diagnostics read.
+__global__ void __launch_bounds__(256) k_gmg_slot_mask(const int *__restrict__ rows, const int *__restrict__ nrows, int T,
+                                                        const float *__restrict__ S, unsigned *__restrict__ mask) {
+    const int n = *nrows;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    unsigned bits0 = 0u, bits1 = 0u, bits2 = 0u;   // bit t: slot lane + 32 t is non-zero in some row of component 0 / 1 / 2
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nwarps) {
+        const int m = rows[r] / T;
+        const float *__restrict__ Sr = S + (size_t)r * GMG_STRIDE;
+        unsigned b = 0u;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int slot = lane + 32 * t;
+            if (slot < GMG_SLOTS && Sr[slot] != 0.0f) b |= 1u << t;
+        }
+        if (m == 0) bits0 |= b; else if (m == 1) bits1 |= b; else bits2 |= b;
+    }
+    for (int t = 0; t < 8; t++) {
+        unsigned w0 = __ballot_sync(0xffffffffu, (bits0 >> t) & 1u), w1 = __ballot_sync(0xffffffffu, (bits1 >> t) & 1u),
+                 w2 = __ballot_sync(0xffffffffu, (bits2 >> t) & 1u);
+        if (lane == 0) {
+            if (w0) atomicOr(&mask[t], w0);
+            if (w1) atomicOr(&mask[8 + t], w1);
+            if (w2) atomicOr(&mask[16 + t], w2);
+        }
+    }
+}
+
+// one CTA of 96 threads: warp m turns the mask of component m into the compact slot list (ascending slot order)
+__global__ void __launch_bounds__(96) k_gmg_compact_table(const unsigned *__restrict__ mask, const int *__restrict__ offs,
+                                                           int *__restrict__ coffs, int *__restrict__ cslot, int *__restrict__ cmeta) {
+    __shared__ int kept[3];
+    const int m = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int base = 0;
+    for (int t = 0; t < 8; t++) {
+        const unsigned w = mask[m * 8 + t];
+        const int pos = base + __popc(w & ((1u << lane) - 1u));
+        if (((w >> lane) & 1u) && pos < GMG_CSTRIDE) {
+            const int slot = lane + 32 * t;
+            cslot[m * GMG_CSTRIDE + pos] = slot;
+            coffs[m * GMG_CSTRIDE + pos] = offs[m * GMG_STRIDE + slot];
+        }
+        base += __popc(w);
+    }
+    for (int j = base + lane; j < GMG_CSTRIDE; j += 32) { cslot[m * GMG_CSTRIDE + j] = -1; coffs[m * GMG_CSTRIDE + j] = 0; }
+    if (lane == 0) { kept[m] = base; cmeta[1 + m] = base; }
+    __syncthreads();
+    if (threadIdx.x == 0) cmeta[0] = (kept[0] <= GMG_CSTRIDE && kept[1] <= GMG_CSTRIDE && kept[2] <= GMG_CSTRIDE) ? 1 : 0;
+}
+
+// one warp per row: Sc[r][j] = S[r][cslot[m][j]]
+__global__ void __launch_bounds__(256) k_gmg_compact_rows(const int *__restrict__ rows, const int *__restrict__ nrows, int T,
+                                                           const float *__restrict__ S, const int *__restrict__ cslot,
+                                                           const int *__restrict__ cmeta, float *__restrict__ Sc) {
+    if (cmeta[0] == 0) return;
+    const int n = *nrows;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nwarps) {
+        const int m = rows[r] / T;
+        const float *__restrict__ Sr = S + (size_t)r * GMG_STRIDE;
+        for (int j = lane; j < GMG_CSTRIDE; j += 32) {
+            const int sl = cslot[m * GMG_CSTRIDE + j];
+            Sc[(size_t)r * GMG_CSTRIDE + j] = sl >= 0 ? Sr[sl] : 0.0f;
+        }
+    }
+}
 
 // ---- x-groups of the first explicit level ---------------------------------------------------------------------------
 // A group = the rows of one 8-cell x-run of a tile (same component, j, k): consecutive rows of the k-plane-major row

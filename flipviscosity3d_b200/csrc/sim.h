@@ -64,6 +64,7 @@ struct Sim {
     int mg_sweeps_l0 = 3, mg_sweeps_l1 = 1;
     int mg_tma = 1;                     // explicit-level sweeps stage their coefficient rows with TMA bulk copies (gmg.h)
     int mg_xgroup = 1;                  // first explicit level: restriction over groups of 8 x-neighbour rows (gmg.h k_gmg_restrict_x)
+    int mg_compact = 1;                 // first explicit level: sweeps read compact rows (160 of 240 slots, gmg.h k_gmg_compact_rows)
     int mg_build = 1;                   // Galerkin products: 1 = gather form (gmg.h k_gmg_build_g), 0 = lane-ordered scatter (bit-identical, slower)
     int mg_dense = 1;                   // exact dense solve on the first level with <= mg_dense_rows rows (else Jacobi sweeps there)
     int mg_dense_rows = 128;            // single-CTA Gauss-Jordan: 0.3 ms at 128 rows, 7 ms at 304 (measured) - keep it small

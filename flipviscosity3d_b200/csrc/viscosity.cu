@@ -377,6 +377,11 @@ static GMG *gmg_get(Sim &s) {
                 heap_alloc(s, L.groups, 3 * T / 8 + 8);
                 heap_alloc(s, L.gtile_off, (size_t)L.ntiles + 1);
                 heap_alloc(s, L.grng, 4);
+                // compact rows (gmg.h k_gmg_compact_rows); the row array itself follows S
+                heap_alloc(s, L.coffs, 3 * GMG_CSTRIDE);
+                heap_alloc(s, L.cslot, 3 * GMG_CSTRIDE);
+                heap_alloc(s, L.cmeta, 4);
+                heap_alloc(s, L.cmask, 3 * 8);
             }
             CUDA_CHECK(cudaStreamSynchronize(s.stream));
             L.owns = true;
@@ -406,6 +411,8 @@ static void gmg_free(Sim &s) {
 static GLevelDev gmg_dev(Sim &s, const GLevel &L, bool own) {
     GLevelDev d;
     d.g = L.g; d.diag = L.diag; d.rows = L.rows; d.nrows = L.nrows_dev; d.S = L.S; d.wj = L.wj; d.offs = L.offs;
+    const bool compact = s.mg_compact && L.cmeta != nullptr && L.Sc != nullptr;
+    d.Sc = compact ? L.Sc : nullptr; d.coffs = compact ? L.coffs : nullptr; d.cmeta = compact ? L.cmeta : nullptr;
     d.rng = own ? L.rng : L.rng + 2;
     d.groups = L.groups;
     d.grng = L.grng ? (own ? L.grng : L.grng + 2) : nullptr;
@@ -478,9 +485,11 @@ static void gmg_build(Sim &s, GMG &M) {
         if (L.nrows == 0) break;
         if ((size_t)L.nrows > L.cap) {
             heap_free(s, L.S); heap_free(s, L.wj);
+            if (L.cmeta) heap_free(s, L.Sc);
             L.cap = (size_t)L.nrows + (size_t)L.nrows / 4 + 1024;
             heap_alloc(s, L.S, L.cap * GMG_STRIDE);   // zero filled: padding slots stay 0
             heap_alloc(s, L.wj, L.cap);
+            if (L.cmeta) heap_alloc(s, L.Sc, L.cap * GMG_CSTRIDE);
             // every rank took this branch (same row count).  The zero fill runs on each rank's own stream: no peer may
             // push rows into the new array before it is done.  A barrier only proves that the peers finished the kernel
             // BEFORE their previous one, so it takes two to order their fills before this rank's push.
@@ -519,6 +528,21 @@ static void gmg_build(Sim &s, GMG &M) {
             s.kernel_launches++;
             M.dense_last = true;
             break;
+        }
+    }
+    // compact rows of the first explicit level for the sweeps (gmg.h): after every reader of the full rows above, on every
+    // rank over all rows (the ranks hold identical rows by now; the pass is ~0.1 ms)
+    if (M.nlevels >= 2 && M.lv[1].cmeta) {
+        GLevel &L = M.lv[1];
+        CUDA_CHECK(cudaMemsetAsync(L.cmeta, 0, 4 * sizeof(int), s.stream));
+        if (s.mg_compact && L.Sc) {
+            CUDA_CHECK(cudaMemsetAsync(L.cmask, 0, 3 * 8 * sizeof(unsigned), s.stream));
+            int GR = gmg_row_grid(s, L);
+            FLIP_LAUNCH_SYNC(k_gmg_slot_mask, GR, 256, s.stream, (const int *)L.rows, (const int *)L.nrows_dev, L.g.total, (const float *)L.S, L.cmask);
+            FLIP_LAUNCH_SYNC(k_gmg_compact_table, 1, 96, s.stream, (const unsigned *)L.cmask, (const int *)L.offs, L.coffs, L.cslot, L.cmeta);
+            FLIP_LAUNCH_SYNC(k_gmg_compact_rows, GR, 256, s.stream, (const int *)L.rows, (const int *)L.nrows_dev, L.g.total, (const float *)L.S,
+                             (const int *)L.cslot, (const int *)L.cmeta, L.Sc);
+            s.kernel_launches += 3;
         }
     }
     KERNEL_CHECK();
@@ -692,11 +716,11 @@ static CGState run_cg_gmg(Sim &s, GMG &M, CGParams P, DiagViscosity diag, double
         auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
         mix((unsigned long long)M.nlevels); mix((unsigned long long)M.dense_last); mix((unsigned long long)chunk); mix((unsigned long long)M.coarse_sweeps);
         mix((unsigned long long)(M.omega * 1e6f)); mix((unsigned long long)P.flexible); mix((unsigned long long)G);
-        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma); mix((unsigned long long)s.mg_xgroup);
+        mix(s.xch_epoch); mix((unsigned long long)s.sharded); mix((unsigned long long)s.mg_tma); mix((unsigned long long)s.mg_xgroup); mix((unsigned long long)s.mg_compact);
         for (int l = 0; l < M.nlevels; l++) {
             const GLevel &L = M.lv[l];
             mix((unsigned long long)M.pre_l[l]); mix((unsigned long long)L.cap); mix((unsigned long long)(size_t)L.S);
-            mix((unsigned long long)(size_t)L.wj); mix((unsigned long long)(size_t)L.x[0]);
+            mix((unsigned long long)(size_t)L.wj); mix((unsigned long long)(size_t)L.x[0]); mix((unsigned long long)(size_t)L.Sc);
         }
         if (M.exec && M.exec_sig != sig) { cudaGraphExecDestroy((cudaGraphExec_t)M.exec); M.exec = nullptr; }
         if (!M.exec) {
@@ -867,6 +891,20 @@ extern "C" int flip_debug_visc_rhs(void *hsim, double *b_host, float *diag_host,
     return 0;
 }
 
+// compact rows of the first explicit level of the last solve (tests / dev tools): meta = {valid, kept slots of component
+// 0, 1, 2}; Sc_out [nrows * GMG_CSTRIDE] and cslot_out [3 * GMG_CSTRIDE] may be null
+extern "C" int flip_debug_gmg_compact(void *hsim, int *meta /*[4]*/, float *Sc_out, int *cslot_out) {
+    Sim &s = *(Sim *)hsim;
+    GMG *M = (GMG *)s.gmg;
+    if (!M || M->nlevels < 2 || !M->lv[1].cmeta) return -1;
+    GLevel &L = M->lv[1];
+    cudaStreamSynchronize(s.stream);
+    if (cudaMemcpy(meta, L.cmeta, 4 * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    if (Sc_out && L.Sc && cudaMemcpy(Sc_out, L.Sc, (size_t)L.nrows * GMG_CSTRIDE * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    if (cslot_out && cudaMemcpy(cslot_out, L.cslot, 3 * GMG_CSTRIDE * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -4;
+    return 0;
+}
+
 // explicit Galerkin level of the last solve (tests / dev tools): rows (m*T + padded id) and S [nrows * GMG_STRIDE]
 extern "C" int flip_debug_gmg_level(void *hsim, int level, int *info /*[10]: ni,nj,nk,ax,ay,az,total,nrows,nlevels,stride*/,
                                     int *rows_out, float *S_out, float *diag_out) {
@@ -914,7 +952,10 @@ int viscosity_time_kernel(Sim &s, const char *name, int reps, float *ms_per_laun
         CUDA_CHECK(cudaEventRecord(e0, s.stream));
         for (int k = 0; k < reps; k++) one(k);
         CUDA_CHECK(cudaEventRecord(e1, s.stream));
-        *alg_bytes = (unsigned long long)L.nrows * (GMG_SLOTS + 5) * 4ull;
+        int meta[4] = {0, 0, 0, 0};
+        if (D.cmeta) CUDA_CHECK(cudaMemcpy(meta, L.cmeta, sizeof(meta), cudaMemcpyDeviceToHost));
+        // stored slots of a row (compact rows: 160, else 240 of which 5 are alignment padding) + row index, weight, b, x in, x out
+        *alg_bytes = (unsigned long long)L.nrows * ((meta[0] ? GMG_CSTRIDE : GMG_SLOTS) + 5) * 4ull;
     } else if (n == "visc_apply") {
         if (s.visc_stats.unknowns == 0) return -1;
         CGParams P = cg_params(s, 0);

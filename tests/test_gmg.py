@@ -159,3 +159,41 @@ def test_time_kernel_reports_the_level1_sweep(cuda_lib, oracle):
     assert ms2 > 0 and nb2 == 32 * sim.stats()["viscosity_unknowns"]
     with pytest.raises(Exception):
         sim.time_kernel("no_such_kernel", 1)
+
+
+def test_compact_rows_of_the_first_explicit_level(lib, oracle):
+    """The sweeps of level 1 read compact rows (csrc/gmg.h k_gmg_compact_rows): every non-zero of a full 235-slot row must
+    be in its 160-slot compact row, at the slot the compact table names, and switching the compact rows off must change
+    nothing but rounding (same iteration count, velocities equal to ~1e-7)."""
+    dll = lib.dll if hasattr(lib, "dll") else lib
+    dll.flip_debug_gmg_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    dll.flip_debug_gmg_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sim, ref = pc.build_pair(lib, oracle, n=32)
+    pc.prepare_mid_substep(sim, ref)
+    out = {}
+    for flag in (0, 1):
+        sim.set_param("mg_compact", flag)
+        out[flag] = _solve(sim, ref, 2)
+        meta = (C.c_int * 4)()
+        assert dll.flip_debug_gmg_compact(sim.h, meta, None, None) == 0
+        assert meta[0] == flag
+    assert out[0][1]["viscosity_iterations"] == out[1][1]["viscosity_iterations"]
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.abs(a - b).max() <= 1e-6
+    info = (C.c_int * 10)()
+    assert dll.flip_debug_gmg_level(sim.h, 1, info, None, None, None) == 0
+    T, nrows, stride = info[6], info[7], info[9]
+    rows = np.zeros(nrows, np.int32); S = np.zeros((nrows, stride), np.float32); d = np.zeros(3 * T, np.float32)
+    assert dll.flip_debug_gmg_level(sim.h, 1, info, rows.ctypes.data, S.ctypes.data, d.ctypes.data) == 0
+    Sc = np.zeros((nrows, 160), np.float32); cslot = np.zeros((3, 160), np.int32)
+    assert dll.flip_debug_gmg_compact(sim.h, meta, Sc.ctypes.data, cslot.ctypes.data) == 0
+    assert max(meta[1], meta[2], meta[3]) <= 160 and min(meta[1], meta[2], meta[3]) > 0
+    comp = rows // T
+    for m in range(3):
+        sl = cslot[m]
+        kept = sl >= 0
+        assert kept.sum() == meta[1 + m] and np.all(np.diff(sl[kept]) > 0)       # ascending slot order, padding last
+        Sm, Scm = S[comp == m], Sc[comp == m]
+        assert np.array_equal(Scm[:, kept], Sm[:, sl[kept]]) and not Scm[:, ~kept].any()
+        dropped = np.setdiff1d(np.arange(235), sl[kept])
+        assert not Sm[:, dropped].any()                                             # nothing non-zero was left behind
