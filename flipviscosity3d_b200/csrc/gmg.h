@@ -778,24 +778,33 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
     __syncthreads();
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     int r = r0 + blockIdx.x * (blockDim.x >> 5) + wid;
-    unsigned phase[2] = {0u, 0u};
+    unsigned phases = 0u;   // bit q: the parity the next wait on barrier q expects (a bit mask: an indexed array would live in local memory)
     int buf = 0;
     if (r < r1 && lane == 0) gmg_bulk_load(Srow[wid][0], Sb + (size_t)r * stride, row_bytes, &bars[wid][0]);
+    int enc = r < r1 ? L.rows[r] : 0;
     for (; r < r1; r += nwarps) {
         const int rn = r + nwarps;
         if (rn < r1 && lane == 0) gmg_bulk_load(Srow[wid][buf ^ 1], Sb + (size_t)rn * stride, row_bytes, &bars[wid][buf ^ 1]);
-        const int enc = L.rows[r];
+        // A warp works on one row at a time, so a row costs the SUM of its dependent memory round trips.  Everything that
+        // does not depend on the product is therefore requested together, before the wait for the coefficient row: the
+        // gathers, the operands of the row update (lane 0) and the index of the NEXT row.
+        const int enc_next = rn < r1 ? L.rows[rn] : 0;
         const int m = enc / L.g.total, id = enc - m * L.g.total;
         const float *__restrict__ xc = xi + id;
-        // the gathers do not depend on the coefficients: issue them before waiting for the row
         float xv[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const int slot = lane + 32 * t;
             xv[t] = slot < stride ? xc[offs[m][slot]] : 0.0f;
         }
-        gmg_bar_wait(&bars[wid][buf], phase[buf]);
-        phase[buf] ^= 1u;
+        float bv = 0.0f, u0 = 0.0f, u1 = 0.0f;
+        if (lane == 0) {
+            bv = b[enc];
+            if (MODE == 1) { u0 = xi[enc]; u1 = L.wj[r]; }
+            else u0 = pn[enc];
+        }
+        gmg_bar_wait(&bars[wid][buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
         const float *Sr = Srow[wid][buf];
         float acc = 0.0f;
 #pragma unroll
@@ -805,11 +814,12 @@ __global__ void __launch_bounds__(256) k_gmg_sweep_tma(GLevelDev L, const float 
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) {
-            if (MODE == 1) out[enc] = xi[enc] + L.wj[r] * (b[enc] - acc);
-            else { float p = pn[enc]; out[enc] = p > 0.0f ? (b[enc] - acc) / p : 0.0f; }
+            if (MODE == 1) out[enc] = u0 + u1 * (bv - acc);
+            else out[enc] = u0 > 0.0f ? (bv - acc) / u0 : 0.0f;
         }
         __syncwarp();   // every lane is done with this buffer before the copy after next overwrites it
         buf ^= 1;
+        enc = enc_next;
     }
     xch_leave(L.X, false);
 }

@@ -154,7 +154,8 @@ def test_time_kernel_reports_the_level1_sweep(cuda_lib, oracle):
     pc.prepare_mid_substep(sim, ref)
     _solve(sim, ref, 2)
     ms, nbytes = sim.time_kernel("gmg_sweep_l1", 5)
-    assert ms > 0 and nbytes > 0 and nbytes % (240 * 4) == 0
+    # rows x (stored slots + 5) x 4 B: 160 stored slots with the compact rows of level 1 (default), else 235
+    assert ms > 0 and nbytes > 0 and (nbytes % (165 * 4) == 0 or nbytes % (240 * 4) == 0)
     ms2, nb2 = sim.time_kernel("visc_apply", 5)
     assert ms2 > 0 and nb2 == 32 * sim.stats()["viscosity_unknowns"]
     with pytest.raises(Exception):
