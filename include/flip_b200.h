@@ -154,8 +154,13 @@ int flip_get_valid(flip_sim *h, int comp, uint8_t *out);
 int flip_set_valid(flip_sim *h, int comp, const uint8_t *in);
 
 /* ---- parameters and diagnostics ----
- * names: "pressure_tol" "pressure_maxit" "viscosity_tol" "viscosity_maxit" "viscosity_accept"
- *        "maxit_scale" "cg_chunk" "pic_ratio" "cfl" "verbose"   (defaults = the reference's)
+ * names: "pressure_tol" "pressure_maxit" "viscosity_tol" "viscosity_maxit" "viscosity_accept" "pic_ratio" "cfl"
+ *        (defaults = the reference's: src/pressuresolver.h:224-226, src/viscositysolver.h:200-202);
+ *        "maxit_scale" (default 40: both solves may take maxit x 40 iterations before the reference's cap / accept /
+ *        fail rule applies - the pressure solve here is diagonal-preconditioned and needs ~7x the reference's MIC(0)
+ *        iterations; 1 = the reference's caps) "cg_chunk" "verbose";
+ *        "mg_compact" 1 = the sweeps of the first explicit multigrid level read compact rows (default), "mg_tma",
+ *        "mg_xgroup", "pressure_resident", "use_block_lists": kernel variants, all on by default, kept switchable for A/B;
  *        "viscosity_precond" 2 = Galerkin multigrid (default), 0 = diagonal;
  *        "viscosity_operator" 0 = rows with the exact face-volume term (default), 1 = rows with the reference's
  *        fp32-rounded diagonal, bit for bit (strict parity in the stiff regime, several times more iterations);
